@@ -1,0 +1,127 @@
+/*
+ * mipb200.h -- C ABI of the B200-native VVC MIP mode-decision engine.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference
+ * (iagostorch/VVC-MIP-GPU) has no FFI layer: its host (main.cpp) drives four OpenCL kernels
+ * through clSetKernelArg/clEnqueueNDRangeKernel.  Each entry point below names the
+ * reference interface it replaces (file:line into the reference repository).
+ *
+ * Conventions: extern "C", plain pointers and sizes, no exceptions across the boundary.
+ * Every function returning int returns 0 on success and a negative MIPB200_E* code on
+ * failure; mipb200_last_error() then holds a human-readable message (thread-local).
+ * One engine drives one GPU.  An engine is not re-entrant; distinct engines may be driven
+ * from distinct threads (one per GPU -- frames are independent, there is no collective).
+ * There is NO CPU fallback: without a CUDA device mipb200_create() fails.
+ */
+#ifndef MIPB200_H
+#define MIPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIPB200_COSTS_PER_CTU 97840 /* (CU,mode) pairs per 128x128 CTU, constants.h:1627-1629 */
+#define MIPB200_CUS_PER_CTU 5380    /* CUs per CTU over the 47 CU types, constants.h:568-570 */
+#define MIPB200_SKIPPED (-1)        /* cost of a CU that is not fully inside the frame
+                                       (the reference leaves garbage there: intra.cl:96,232,717) */
+
+/* error codes */
+#define MIPB200_OK 0
+#define MIPB200_EINVAL (-1)   /* bad argument / unsupported geometry */
+#define MIPB200_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define MIPB200_ENODEV (-3)   /* no usable CUDA device */
+#define MIPB200_EBUSY (-4)    /* submit with all slots in flight */
+#define MIPB200_EEMPTY (-5)   /* collect with nothing in flight */
+#define MIPB200_ENOMEM (-6)
+
+/* what a frame's result carries (mipb200_config.emit bitmask) */
+#define MIPB200_EMIT_COSTS 1u      /* int32 cost[nCTU][97840] = min(2*SAD, SATD), reference order */
+#define MIPB200_EMIT_SAD_SATD 2u   /* int32 sad[...] and satd[...] in the same layout */
+#define MIPB200_EMIT_DECISIONS 4u  /* uint8 best_mode[nCTU][5380] + int32 best_cost[nCTU][5380] */
+
+/* filter_type: 0 = original samples (USE_ALTERNATIVE_SAMPLES 0, main.cpp:10);
+ * 1..8 = the reference's availableFilters in order (constants.h:25-34):
+ *   1 filterFrame_1d_int            2 filterFrame_1d_float
+ *   3 filterFrame_2d_int_quarterCtu 4 filterFrame_2d_float_quarterCtu
+ *   5 filterFrame_1d_int_5x5        6 filterFrame_1d_float_5x5
+ *   7 filterFrame_2d_int_5x5_quarterCtu  8 filterFrame_2d_float_5x5_quarterCtu */
+typedef struct mipb200_config {
+    int width, height; /* luma size; width % 128 == 0, height % 4 == 0 (main.cpp:289-309) */
+    int device;        /* CUDA ordinal == --DeviceIndex (main.cpp:221-228) */
+    int filter_type;   /* 0..8, see above (--FilterType, main.cpp:57) */
+    int kernel_idx;    /* --KernelIdx (main.cpp:58): 0..4 for 3x3 filters, 0..2 for 5x5 */
+    int slots;         /* frames in flight (>= 1; the reference has BUFFER_SLOTS 2, intra.cl:12) */
+    unsigned emit;     /* MIPB200_EMIT_* bitmask, must not be 0 */
+} mipb200_config;
+
+typedef struct mipb200_engine mipb200_engine;
+
+/* Result of one frame; pointers address the engine's pinned host ring and stay valid until
+ * the next mipb200_collect()/mipb200_destroy() on the same engine.  Unrequested outputs are
+ * NULL.  Replaces return_minSadHad/SAD/SATD (main.cpp:660, main_aux_functions.h:585-630). */
+typedef struct mipb200_result {
+    int64_t poc;              /* tag given at submit */
+    int n_ctus;               /* ceil(W/128) * ceil(H/128), raster order (intra.cl:44-45) */
+    const int32_t* cost;      /* [n_ctus][97840] */
+    const int32_t* sad;       /* [n_ctus][97840] */
+    const int32_t* satd;      /* [n_ctus][97840] */
+    const uint8_t* best_mode; /* [n_ctus][5380]; argmin over modes, lowest wins ties; 0xFF if skipped */
+    const int32_t* best_cost; /* [n_ctus][5380] */
+    float gpu_ms;             /* device time of this frame's kernels (CUDA events) */
+} mipb200_result;
+
+/* Replaces the OpenCL platform/context/queue/buffer/program setup, main.cpp:87-315, 408-549. */
+int mipb200_create(mipb200_engine** out, const mipb200_config* cfg);
+void mipb200_destroy(mipb200_engine* e);
+
+/* Pinned staging buffer (width*height uint16) of the slot the next submit will use.  Filling
+ * it directly and passing the same pointer to mipb200_submit() avoids one host copy.
+ * Returns NULL when every slot is in flight. */
+uint16_t* mipb200_next_input(mipb200_engine* e);
+
+/* Enqueue one frame: async H2D from the pinned slot, filter (if any), MIP costs, decisions,
+ * async D2H.  `frame` = height*width uint16 row-major, samples 0..1023 (main.cpp:364-384);
+ * it is copied into the pinned slot unless it already is mipb200_next_input().  Returns
+ * immediately.  Replaces one iteration of the frame loop, main.cpp:678-1241. */
+int mipb200_submit(mipb200_engine* e, const uint16_t* frame, int64_t poc);
+
+/* Wait for the oldest frame in flight and expose its results (FIFO).
+ * Replaces clFinish + readMemobjsIntoArray_Distortion, main.cpp:1223-1250. */
+int mipb200_collect(mipb200_engine* e, mipb200_result* out);
+
+int mipb200_in_flight(const mipb200_engine* e);
+int mipb200_num_ctus(int width, int height);
+
+/* Device-resident path: the frame is already in HBM and the results stay there (no host
+ * copies).  All pointers are device pointers on the engine's GPU; any output may be NULL.
+ * `stream` is a cudaStream_t (NULL = the engine's compute stream).  Asynchronous.
+ * This is the fused equivalent of the reference's kernel sequence filterFrame_* ->
+ * initBoundaries -> MIP_ReducedPred -> upsampleDistortion x3 (main.cpp:723-742, 819-844,
+ * 925-946, 1011-1045, 1090-1124, 1167-1200). */
+int mipb200_run_device(mipb200_engine* e, const uint16_t* d_frame, int32_t* d_cost, int32_t* d_sad,
+                       int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, void* stream);
+
+/* Only the low-pass filter: d_out[h][w] = filtered d_frame.  Same arguments as the
+ * reference's filterFrame_* kernels (intra.cl:1639, 1828, 2311, 2539, 2856, 3042, 3267, 3508:
+ * referenceFrame, filteredFrame, frameWidth, frameHeight, kernelIdx). */
+int mipb200_filter_device(mipb200_engine* e, const uint16_t* d_frame, uint16_t* d_out, void* stream);
+
+/* Per CU argmin over an existing cost table (device pointers). */
+int mipb200_decide_device(mipb200_engine* e, const int32_t* d_cost, uint8_t* d_best_mode,
+                          int32_t* d_best_cost, void* stream);
+
+/* Number of this library's kernels launched so far on this engine (bench.py: gpu_launches). */
+long long mipb200_kernel_launches(const mipb200_engine* e);
+
+/* Block until everything enqueued on the engine's streams has finished. */
+int mipb200_sync(mipb200_engine* e);
+
+const char* mipb200_last_error(void);
+const char* mipb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIPB200_H */

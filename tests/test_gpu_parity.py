@@ -1,0 +1,117 @@
+"""CUDA engine vs the CPU oracle through the C ABI: bit-exact costs (integer work).
+
+Sizes are chosen so that the oracle finishes in seconds: 256x256 (all four frame-edge
+rules, 4 CTUs), 256x184 (partial bottom CTU row, 56 valid rows like 1080p), 384x128.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(mip, frame, ft=0, kidx=0, emit=None):
+    h, w = frame.shape
+    emit = emit if emit is not None else (mip.EMIT_COSTS | mip.EMIT_SAD_SATD | mip.EMIT_DECISIONS)
+    with mip.Engine(w, h, filter_type=ft, kernel_idx=kidx, slots=2, emit=emit) as eng:
+        r = eng.run(frame)
+        return {k: (None if getattr(r, k) is None else getattr(r, k).copy()) for k in ("cost", "sad", "satd", "best_mode", "best_cost")}
+
+
+def _assert_same(got, want, what):
+    if not np.array_equal(got, want):
+        bad = np.argwhere(got != want)
+        raise AssertionError(f"{what}: {len(bad)} of {want.size} differ; first {bad[:5].tolist()} got {got[tuple(bad[0])]} want {want[tuple(bad[0])]}")
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (184, 256), (128, 384)])
+@pytest.mark.parametrize("content", ["kat", "noise", "natural", "checker", "zeros", "ones"])
+def test_costs_original_samples(mip, oracle, shape, content):
+    from mipb200 import frames
+    h, w = shape
+    f = {"kat": lambda: frames.kat_frame(w, h), "noise": lambda: frames.noise_frame(w, h, 1),
+         "natural": lambda: frames.natural_frame(w, h, 2), "checker": lambda: frames.extreme_frame(w, h, 2),
+         "zeros": lambda: frames.extreme_frame(w, h, 0), "ones": lambda: frames.extreme_frame(w, h, 1)}[content]()
+    got = _run(mip, f)
+    cost, sad, satd = oracle.run_frame(f, want_sad_satd=True)
+    _assert_same(got["cost"], cost, "cost")
+    _assert_same(got["sad"], sad, "sad")
+    _assert_same(got["satd"], satd, "satd")
+    bm, bc = oracle.decisions(cost)
+    _assert_same(got["best_mode"], bm, "best_mode")
+    _assert_same(got["best_cost"], bc, "best_cost")
+
+
+@pytest.mark.parametrize("ft", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_costs_all_filters_all_kernel_idx(mip, oracle, ft):
+    from mipb200 import frames, tables
+    f = frames.noise_frame(256, 184, 7)
+    for kidx in range(tables.num_kernel_idx(ft)):
+        got = _run(mip, f, ft, kidx, emit=mip.EMIT_COSTS)
+        _assert_same(got["cost"], oracle.run_frame(f, ft, kidx), f"cost ft={ft} kidx={kidx}")
+
+
+@pytest.mark.parametrize("ft", [1, 3, 5, 7])
+def test_filter_only(mip, oracle, ft):
+    import torch
+    from mipb200 import frames, tables
+    f = frames.natural_frame(256, 88, 3)
+    for kidx in range(tables.num_kernel_idx(ft)):
+        with mip.Engine(256, 88, filter_type=ft, kernel_idx=kidx, slots=1) as eng:
+            d_in = torch.from_numpy(f.view(np.int16)).cuda()
+            d_out = torch.empty_like(d_in)
+            eng.filter_device(d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy().view(np.uint16)
+        _assert_same(got, oracle.filter_frame(f, ft, kidx), f"filter ft={ft} kidx={kidx}")
+
+
+def test_pipelined_frames_fifo_and_determinism(mip, oracle):
+    """3 slots, 7 frames in flight-order; results come back FIFO and equal the oracle."""
+    from mipb200 import frames
+    fs = [frames.noise_frame(256, 128, 10 + i) for i in range(7)]
+    want = [oracle.run_frame(f) for f in fs]
+    with mip.Engine(256, 128, slots=3, emit=mip.EMIT_COSTS) as eng:
+        got, sub = [], 0
+        while len(got) < len(fs):
+            while sub < len(fs) and eng.in_flight() < 3:
+                buf = eng.next_input()
+                buf[...] = fs[sub]
+                eng.submit(buf, poc=sub)
+                sub += 1
+            r = eng.collect()
+            assert r.poc == len(got)
+            got.append(r.cost.copy())
+    for g, w in zip(got, want):
+        _assert_same(g, w, "pipelined cost")
+
+
+def test_device_resident_path(mip, oracle):
+    import torch
+    from mipb200 import frames
+    f = frames.natural_frame(256, 256, 5)
+    with mip.Engine(256, 256, slots=1) as eng:
+        d_in = torch.from_numpy(f.view(np.int16)).cuda()
+        d_cost = torch.empty((eng.n_ctus, mip.COSTS_PER_CTU), dtype=torch.int32, device="cuda")
+        d_bm = torch.empty((eng.n_ctus, mip.CUS_PER_CTU), dtype=torch.uint8, device="cuda")
+        d_bc = torch.empty((eng.n_ctus, mip.CUS_PER_CTU), dtype=torch.int32, device="cuda")
+        n0 = eng.kernel_launches()
+        eng.run_device(d_in.data_ptr(), d_cost.data_ptr(), d_best_mode=d_bm.data_ptr(), d_best_cost=d_bc.data_ptr(),
+                       stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert eng.kernel_launches() - n0 == 2
+        want = oracle.run_frame(f)
+        _assert_same(d_cost.cpu().numpy(), want, "device cost")
+        bm, bc = oracle.decisions(want)
+        _assert_same(d_bm.cpu().numpy(), bm, "device best_mode")
+
+
+def test_errors(mip):
+    with pytest.raises(mip.MipError):
+        mip.Engine(250, 128)
+    with pytest.raises(mip.MipError):
+        mip.Engine(256, 128, filter_type=9)
+    with pytest.raises(mip.MipError):
+        mip.Engine(256, 128, filter_type=5, kernel_idx=3)
+    with mip.Engine(256, 128, slots=1) as eng:
+        with pytest.raises(mip.MipError):
+            eng.collect()

@@ -1,0 +1,401 @@
+// main.cpp -- command-line host of the B200 MIP engine; drop-in for the reference's ./main.
+//
+// Same surface as the reference host (main.cpp:43-85 CLI, :364-384 CSV input,
+// main_aux_functions.h:735-798 cost log, :908-914 timing block):
+//
+//   ./mipb200_main -f N -s WxH -o frames.csv [-l prefix] [--DeviceIndex i]
+//                  [--FilterType name] [--KernelIdx k]
+//
+// Long options accept any unique prefix (boost::program_options' default "guessing"), so the
+// README's --Filter=... works; values may follow as "--Opt=value" or "--Opt value".
+// USE_ALTERNATIVE_SAMPLES is the reference's compile-time switch (main.cpp:10); here it is the
+// default of the run-time option --UseAlternativeSamples (0|1).
+// Extensions (all off by default): --NumGpus G (frames sharded poc % G over G GPUs, one host
+// thread each, no collective), --AllFrames (log every frame with a leading POC column),
+// --Compat (print 0 in the SAD/SATD columns like the reference's MAX_PERFORMANCE_DIST build),
+// --NoLog (skip the text log).
+//
+// The device work goes through the C ABI of include/mipb200.h only.
+#include <errno.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+#include <time.h>
+
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/mipb200.h"
+#include "mip_tables.h"
+
+#ifndef USE_ALTERNATIVE_SAMPLES
+#define USE_ALTERNATIVE_SAMPLES 0
+#endif
+#ifndef TRACE_POWER
+#define TRACE_POWER 1   // the reference ships with TRACE_POWER 1 (main_aux_functions.h:3)
+#endif
+
+namespace {
+
+struct Options {
+    int deviceIndex = 0;   bool deviceSet = false;
+    int nFrames = -1;      bool framesSet = false;
+    std::string resolution;
+    std::string input;     bool inputSet = false;
+    std::string prefix;    bool prefixSet = false;
+    std::string filter;    bool filterSet = false;
+    int kernelIdx = 0;     bool kernelSet = false;
+    int useAlt = USE_ALTERNATIVE_SAMPLES;
+    int numGpus = 1;
+    bool allFrames = false, compat = false, noLog = false, help = false;
+};
+
+const char* kLongOpts[] = {"help", "DeviceIndex", "FramesToBeEncoded", "Resolution", "OriginalFrames", "OutputPreffix",
+                           "FilterType", "KernelIdx", "UseAlternativeSamples", "NumGpus", "AllFrames", "Compat", "NoLog"};
+const bool kTakesValue[] = {false, true, true, true, true, true, true, true, true, true, false, false, false};
+constexpr int kNumOpts = sizeof(kLongOpts) / sizeof(kLongOpts[0]);
+
+void print_help() {
+    printf("Allowed options:\n"
+           "  -h [ --help ]                  produce help message\n"
+           "  --DeviceIndex arg (=0)         Index of the GPU device (CUDA ordinal)\n"
+           "  -f [ --FramesToBeEncoded ] arg Number of frames to be processed\n"
+           "  -s [ --Resolution ] arg        Resolution of the video, in the format 1920x1080\n"
+           "  -o [ --OriginalFrames ] arg    Input file for original frames samples\n"
+           "  -l [ --OutputPreffix ] arg     Output files preffix with produced costs\n"
+           "  --FilterType arg               Type of smoothing filter\n"
+           "  --KernelIdx arg (=0)           Index of the filtering kernel used to define the coefficients\n"
+           "  --UseAlternativeSamples arg    0|1, run-time form of the USE_ALTERNATIVE_SAMPLES macro\n"
+           "  --NumGpus arg (=1)             shard frames over this many GPUs\n"
+           "  --AllFrames --Compat --NoLog   log every frame / zero SAD,SATD columns / no text log\n");
+}
+
+// resolves a (possibly abbreviated) long option; -1 unknown, -2 ambiguous
+int match_long(const std::string& name) {
+    int hit = -1;
+    for (int i = 0; i < kNumOpts; ++i) {
+        if (name == kLongOpts[i]) return i;
+        if (strncmp(kLongOpts[i], name.c_str(), name.size()) == 0) {
+            if (hit >= 0) return -2;
+            hit = i;
+        }
+    }
+    return hit;
+}
+
+bool to_int(const std::string& s, int* v) {
+    char* end = nullptr;
+    errno = 0;
+    long x = strtol(s.c_str(), &end, 10);
+    if (errno || end == s.c_str() || *end) return false;
+    *v = (int)x;
+    return true;
+}
+
+bool parse_args(int argc, char** argv, Options& o) {
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        int opt = -1;
+        std::string val;
+        bool haveVal = false;
+        if (a.rfind("--", 0) == 0) {
+            std::string name = a.substr(2);
+            size_t eq = name.find('=');
+            if (eq != std::string::npos) { val = name.substr(eq + 1); name = name.substr(0, eq); haveVal = true; }
+            opt = match_long(name);
+            if (opt == -1) { fprintf(stderr, "unrecognised option '--%s'\n", name.c_str()); return false; }
+            if (opt == -2) { fprintf(stderr, "option '--%s' is ambiguous\n", name.c_str()); return false; }
+        } else if (a.size() >= 2 && a[0] == '-') {
+            switch (a[1]) {
+                case 'h': opt = 0; break;
+                case 'f': opt = 2; break;
+                case 's': opt = 3; break;
+                case 'o': opt = 4; break;
+                case 'l': opt = 5; break;
+                default: fprintf(stderr, "unrecognised option '%s'\n", a.c_str()); return false;
+            }
+            if (a.size() > 2) { val = a.substr(a[2] == '=' ? 3 : 2); haveVal = true; }
+        } else {
+            fprintf(stderr, "too many positional options have been specified on the command line\n");
+            return false;
+        }
+        if (kTakesValue[opt] && !haveVal) {
+            if (i + 1 >= argc) { fprintf(stderr, "the required argument for option '--%s' is missing\n", kLongOpts[opt]); return false; }
+            val = argv[++i];
+        }
+        bool ok = true;
+        switch (opt) {
+            case 0: o.help = true; break;
+            case 1: ok = to_int(val, &o.deviceIndex); o.deviceSet = true; break;
+            case 2: ok = to_int(val, &o.nFrames); o.framesSet = true; break;
+            case 3: o.resolution = val; break;
+            case 4: o.input = val; o.inputSet = true; break;
+            case 5: o.prefix = val; o.prefixSet = true; break;
+            case 6: o.filter = val; o.filterSet = true; break;
+            case 7: ok = to_int(val, &o.kernelIdx); o.kernelSet = true; break;
+            case 8: ok = to_int(val, &o.useAlt); break;
+            case 9: ok = to_int(val, &o.numGpus); break;
+            case 10: o.allFrames = true; break;
+            case 11: o.compat = true; break;
+            case 12: o.noLog = true; break;
+        }
+        if (!ok) { fprintf(stderr, "the argument ('%s') for option '--%s' is invalid\n", val.c_str(), kLongOpts[opt]); return false; }
+    }
+    return true;
+}
+
+// parameter echo of checkReportParameters (main_aux_functions.h:113-162)
+int report_parameters(const Options& o) {
+    int errors = 0;
+    printf("-=-= INPUT PARAMETERS =-=-\n");
+    if (!o.deviceSet) printf("  Device index not set. Using standard value of %d.\n", o.deviceIndex);
+    else printf("  Device Index=%d\n", o.deviceIndex);
+    if (!o.prefixSet) printf("  OutputPreffix log file not set. The output will not be written to any file.\n");
+    else printf("  OutputPreffix=%s\n", o.prefix.c_str());
+    if (o.framesSet) printf("  FramesToBeEncoded=%d\n", o.nFrames);
+    else { printf("  [!] ERROR: FramesToBeEncoded not set.\n"); errors++; }
+    if (o.inputSet) printf("  InputOriginalFrame=%s\n", o.input.c_str());
+    else { printf("  [!] ERROR: Input original frames not set.\n"); errors++; }
+    if (o.useAlt) {
+        if (o.filterSet) printf("  FilterType=%s\n", o.filter.c_str());
+        else { printf("  [!] ERROR: Filter not set.\n"); errors++; }
+        if (!o.kernelSet) printf("  KernelIdx not set. Using default value zero.\n");
+        else printf("  KernelIdx=%d\n", o.kernelIdx);
+    }
+    return errors;
+}
+
+void print_timestamp(const char* what) {  // main_aux_functions.h:180-189
+    if (!TRACE_POWER) return;
+    struct timeval tv;
+    gettimeofday(&tv, nullptr);
+    struct tm* t = localtime(&tv.tv_sec);
+    printf("%s @ %02d:%02d:%02d.%03d\n", what, t->tm_hour, t->tm_min, t->tm_sec, (int)(tv.tv_usec / 1000));
+}
+
+double now_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+// CSV reader (main.cpp:364-384): N*H lines of W comma-separated integers; extra fields ignored.
+bool read_frames_csv(const std::string& path, int W, int H, int N, std::vector<uint16_t>& out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { perror("error while opening samples files"); return false; }
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<char> buf((size_t)sz + 1);
+    if (fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); fprintf(stderr, "short read on %s\n", path.c_str()); return false; }
+    fclose(f);
+    buf[sz] = '\n';
+    out.resize((size_t)W * H * N);
+    const char* p = buf.data();
+    const char* end = p + sz;
+    for (long line = 0; line < (long)N * H; ++line) {
+        if (p >= end) { fprintf(stderr, "[!] ERROR: %s holds %ld lines, need %ld (%d frames of %d rows)\n", path.c_str(), line, (long)N * H, N, H); return false; }
+        uint16_t* dst = out.data() + (size_t)line * W;
+        for (int x = 0; x < W; ++x) {
+            while (p < end && (*p == ' ' || *p == '\t')) ++p;
+            if (p >= end || *p < '0' || *p > '9') {
+                fprintf(stderr, "[!] ERROR: line %ld of %s: field %d is not a number (need %d samples per line)\n", line + 1, path.c_str(), x + 1, W);
+                return false;
+            }
+            int v = 0;
+            while (*p >= '0' && *p <= '9') v = v * 10 + (*p++ - '0');
+            dst[x] = (uint16_t)v;
+            if (*p == ',') ++p;
+        }
+        while (p < end && *p != '\n') ++p;
+        ++p;
+    }
+    return true;
+}
+
+// ---- cost log (main_aux_functions.h:735-798)
+struct LogBuf {
+    FILE* f;
+    std::vector<char> b;
+    size_t n = 0;
+    explicit LogBuf(FILE* fp) : f(fp), b(8u << 20) {}
+    void flush() { if (n) fwrite(b.data(), 1, n, f); n = 0; }
+    void ensure(size_t k) { if (n + k > b.size()) flush(); }
+    void put(const char* s, size_t k) { memcpy(b.data() + n, s, k); n += k; }
+    void put_int(long v) {
+        char t[24];
+        int k = 0;
+        bool neg = v < 0;
+        unsigned long u = neg ? (unsigned long)(-v) : (unsigned long)v;
+        do { t[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+        if (neg) b[n++] = '-';
+        while (k) b[n++] = t[--k];
+    }
+};
+
+void write_frame_log(LogBuf& lb, long poc, bool withPoc, const int32_t* cost, const int32_t* sad, const int32_t* satd,
+                     int nCtus, int W, bool compat) {
+    const int ctuCols = (W + 127) / 128;
+    for (int ctu = 0; ctu < nCtus; ++ctu) {
+        const int ctuX = 128 * (ctu % ctuCols), ctuY = 128 * (ctu / ctuCols);
+        for (int t = 0; t < MIP_NUM_TYPES; ++t) {   // SizeId 2 types, then SizeId 1, then 4x4: the table order
+            const mip_cu_type_t& ty = MIP_TYPES[t];
+            for (int cu = 0; cu < ty.n; ++cu) {
+                char pre[160];
+                int pl = 0;
+                if (withPoc) pl += snprintf(pre + pl, sizeof(pre) - pl, "%ld,", poc);
+                pl += snprintf(pre + pl, sizeof(pre) - pl, "%d,%s,%d,%d,%d,%d,%d,", ctu, ty.name, ty.w, ty.h, cu,
+                               ctuX + ty.xs[cu % ty.cols], ctuY + ty.ys[cu / ty.cols]);
+                const size_t base = (size_t)ctu * MIP_COSTS_PER_CTU + ty.cost_off + (size_t)cu * ty.modes;
+                for (int m = 0; m < ty.modes; ++m) {
+                    lb.ensure(256);
+                    lb.put(pre, pl);
+                    lb.put_int(m); lb.b[lb.n++] = ',';
+                    lb.put_int(compat || !sad ? 0 : sad[base + m]); lb.b[lb.n++] = ',';
+                    lb.put_int(compat || !satd ? 0 : satd[base + m]); lb.b[lb.n++] = ',';
+                    lb.put_int(cost[base + m]); lb.b[lb.n++] = '\n';
+                }
+            }
+        }
+    }
+}
+
+struct Shared {
+    Options opt;
+    int W = 0, H = 0, nCtus = 0, filterType = 0;
+    const uint16_t* frames = nullptr;
+    std::vector<std::vector<int32_t>> keepCost, keepSad, keepSatd;  // per frame, only those that get logged
+    std::atomic<int> errors{0};
+};
+
+// one host thread per GPU: frames poc = g, g+G, g+2G, ...
+void gpu_worker(Shared* sh, int g, int G) {
+    const Options& o = sh->opt;
+    mipb200_config cfg;
+    cfg.width = sh->W; cfg.height = sh->H; cfg.device = o.deviceIndex + g;
+    cfg.filter_type = sh->filterType; cfg.kernel_idx = o.kernelIdx; cfg.slots = 3;
+    const bool wantLog = !o.noLog;
+    cfg.emit = MIPB200_EMIT_COSTS | (wantLog && !o.compat ? MIPB200_EMIT_SAD_SATD : 0);
+    mipb200_engine* e = nullptr;
+    if (mipb200_create(&e, &cfg) != 0) {
+        fprintf(stderr, "[!] ERROR (GPU %d): %s\n", cfg.device, mipb200_last_error());
+        sh->errors++;
+        return;
+    }
+    const size_t fpx = (size_t)sh->W * sh->H, ncost = (size_t)sh->nCtus * MIP_COSTS_PER_CTU;
+    int next = g, done = g;
+    auto collect_one = [&]() -> bool {
+        mipb200_result r;
+        if (mipb200_collect(e, &r) != 0) { fprintf(stderr, "[!] ERROR (GPU %d): %s\n", cfg.device, mipb200_last_error()); sh->errors++; return false; }
+        const int poc = (int)r.poc;
+        if (wantLog && (poc == 0 || o.allFrames)) {   // the reference exports frame 0 only (main.cpp:1268)
+            sh->keepCost[poc].assign(r.cost, r.cost + ncost);
+            if (r.sad) { sh->keepSad[poc].assign(r.sad, r.sad + ncost); sh->keepSatd[poc].assign(r.satd, r.satd + ncost); }
+        }
+        done += G;
+        return true;
+    };
+    while (done < o.nFrames) {
+        while (next < o.nFrames && mipb200_in_flight(e) < cfg.slots) {
+            if (G == 1) printf("Current frame %d\n", next);
+            if (mipb200_submit(e, sh->frames + fpx * next, next) != 0) {
+                fprintf(stderr, "[!] ERROR (GPU %d): %s\n", cfg.device, mipb200_last_error());
+                sh->errors++;
+                mipb200_destroy(e);
+                return;
+            }
+            next += G;
+        }
+        if (!collect_one()) break;
+    }
+    mipb200_destroy(e);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Shared sh;
+    Options& o = sh.opt;
+    if (!parse_args(argc, argv, o)) return 1;
+    if (o.help) { print_help(); return 1; }
+
+    int po_error = report_parameters(o);
+    if (o.useAlt) {
+        int ft = 0;
+        for (int i = 0; i < 8; ++i)
+            if (o.filter == MIP_FILTER_NAMES[i]) ft = i + 1;
+        if (!ft) {   // main.cpp:74-77
+            printf("  [!] ERROR: Filter type %s not supported\n", o.filter.c_str());
+            return 0;
+        }
+        sh.filterType = ft;
+    }
+    if (po_error > 0) {
+        printf("Exiting after finding errors in input parameters\n");
+        return 1;
+    }
+    print_timestamp("STARTED HOST");
+
+    int W = 0, H = 0;
+    {
+        size_t x = o.resolution.find('x');
+        if (x == std::string::npos || !to_int(o.resolution.substr(0, x), &W) || !to_int(o.resolution.substr(x + 1), &H)) {
+            printf("  [!] ERROR: Input resolution \"%s\" not set properly\n", o.resolution.c_str());
+            return 0;
+        }
+    }
+    if (W <= 0 || H <= 0 || W % 128 != 0 || H % 4 != 0) {
+        printf("[!] ERROR: Unsupported resolution %dx%d\n", W, H);
+        printf("Supported resolutions are: any WxH with W %% 128 == 0 and H %% 4 == 0, e.g.\n  3840x2160\n  1920x1080\n  1280x720\n");
+        return 0;
+    }
+    if (o.nFrames < 1 || o.numGpus < 1) { printf("  [!] ERROR: FramesToBeEncoded and NumGpus must be positive\n"); return 1; }
+    sh.W = W; sh.H = H; sh.nCtus = mipb200_num_ctus(W, H);
+
+    print_timestamp("START READ SAMPLES .csv");
+    std::vector<uint16_t> frames;
+    if (!read_frames_csv(o.input, W, H, o.nFrames, frames)) return 1;
+    print_timestamp("FINISH READ SAMPLES .csv");
+    sh.frames = frames.data();
+    sh.keepCost.resize(o.nFrames); sh.keepSad.resize(o.nFrames); sh.keepSatd.resize(o.nFrames);
+
+    // ---- timed window: first upload -> last result resident on the host (main.cpp:566-569, 1247-1250)
+    print_timestamp("START WRITE SAMPLES MEMOBJ");
+    const double t0 = now_ms();
+    {
+        std::vector<std::thread> th;
+        for (int g = 0; g < o.numGpus; ++g) th.emplace_back(gpu_worker, &sh, g, o.numGpus);
+        for (auto& t : th) t.join();
+    }
+    const double t1 = now_ms();
+    print_timestamp("FINISH READ DISTORTION");
+    if (sh.errors) return 1;
+
+    if (!o.noLog) {
+        // like the reference, a log is written even when -l is omitted (file ".csv", main.cpp:1264-1269)
+        std::string name = o.prefix + ".csv";
+        FILE* f = fopen(name.c_str(), "w");
+        if (!f) { perror("error while opening the output file"); return 1; }
+        LogBuf lb(f);
+        const char* hdr = o.allFrames ? "POC,CTU,cuSizeName,W,H,CU,X,Y,Mode,SAD,SATD,minSadHad\n" : "CTU,cuSizeName,W,H,CU,X,Y,Mode,SAD,SATD,minSadHad\n";
+        lb.put(hdr, strlen(hdr));
+        for (int poc = 0; poc < (o.allFrames ? o.nFrames : 1); ++poc)
+            write_frame_log(lb, poc, o.allFrames, sh.keepCost[poc].data(), sh.keepSad[poc].empty() ? nullptr : sh.keepSad[poc].data(),
+                            sh.keepSatd[poc].empty() ? nullptr : sh.keepSatd[poc].data(), sh.nCtus, W, o.compat);
+        lb.flush();
+        fclose(f);
+    }
+
+    // reportTimingResults_Compact (main_aux_functions.h:908-914)
+    printf("=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=\n");
+    printf("TIMING RESULTS (miliseconds)\n");
+    printf("Elapsed time (ms) from writing samples to reading distortion (%dx), %d\n", o.nFrames, (int)lround(t1 - t0));
+    printf("=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=\n\n");
+    printf("Throughput: %.1f frames/s on %d GPU(s)\n", o.nFrames * 1e3 / (t1 - t0 > 0 ? t1 - t0 : 1e-3), o.numGpus);
+    print_timestamp("FINISHED HOST");
+    return 0;
+}

@@ -1,0 +1,293 @@
+// mip_engine.cu -- C ABI (include/mipb200.h) on top of the kernels: pinned host rings, one
+// CUDA stream per slot so that H2D of frame f+1, the kernels of frame f and D2H of frame f-1
+// overlap, FIFO collection.  Replaces the reference's OpenCL host plumbing (main.cpp:87-315,
+// 408-457, 560-598, 678-1250; main_aux_functions.h:585-630).  No CPU fallback exists.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/mipb200.h"
+#include "mip_kernels.h"
+#include "mip_tables.h"
+
+#define MIPB200_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(call)                                                                         \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return fail(MIPB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    uint16_t* h_frame = nullptr;  // pinned
+    uint16_t *d_frame = nullptr, *d_filt = nullptr;
+    int32_t *d_cost = nullptr, *d_sad = nullptr, *d_satd = nullptr, *d_best_cost = nullptr;
+    uint8_t* d_best_mode = nullptr;
+    int32_t *h_cost = nullptr, *h_sad = nullptr, *h_satd = nullptr, *h_best_cost = nullptr;  // pinned
+    uint8_t* h_best_mode = nullptr;
+    int64_t poc = 0;
+    bool busy = false;
+};
+
+std::mutex g_init_mutex;
+bool g_dev_init[64] = {false};
+
+}  // namespace
+
+struct mipb200_engine {
+    mipb200_config cfg;
+    int n_ctus = 0;
+    size_t frame_bytes = 0, cost_bytes = 0, cu_bytes4 = 0, cu_bytes1 = 0;
+    std::vector<Slot> slots;
+    int head = 0;   // next slot to submit into
+    int tail = 0;   // oldest slot in flight
+    int in_flight = 0;
+    long long launches = 0;
+    cudaStream_t aux_stream = nullptr;
+    uint16_t* d_aux_filt = nullptr;   // scratch filtered frame for mipb200_run_device
+};
+
+MIPB200_API const char* mipb200_last_error(void) { return g_err; }
+MIPB200_API const char* mipb200_version(void) { return "mipb200 0.1 (sm_100a)"; }
+MIPB200_API int mipb200_num_ctus(int w, int h) { return ((w + 127) / 128) * ((h + 127) / 128); }
+
+static int check_cfg(const mipb200_config* c) {
+    if (!c) return fail(MIPB200_EINVAL, "config is NULL");
+    if (c->width <= 0 || c->height <= 0 || c->width % 128 != 0 || c->height % 4 != 0)
+        return fail(MIPB200_EINVAL, "unsupported resolution %dx%d (need width %% 128 == 0, height %% 4 == 0)", c->width, c->height);
+    if (c->filter_type < 0 || c->filter_type > 8) return fail(MIPB200_EINVAL, "filter_type %d out of range 0..8", c->filter_type);
+    if (c->filter_type > 0) {
+        const int nk = c->filter_type >= 5 ? 3 : 5;
+        if (c->kernel_idx < 0 || c->kernel_idx >= nk)
+            return fail(MIPB200_EINVAL, "kernel_idx %d out of range 0..%d for filter %s", c->kernel_idx, nk - 1,
+                        MIP_FILTER_NAMES[c->filter_type - 1]);
+    }
+    if (c->slots < 1 || c->slots > 16) return fail(MIPB200_EINVAL, "slots %d out of range 1..16", c->slots);
+    if (c->emit == 0 || (c->emit & ~7u)) return fail(MIPB200_EINVAL, "emit mask 0x%x invalid", c->emit);
+    return MIPB200_OK;
+}
+
+static void free_slot(Slot& s) {
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    cudaFreeHost(s.h_frame); cudaFreeHost(s.h_cost); cudaFreeHost(s.h_sad); cudaFreeHost(s.h_satd);
+    cudaFreeHost(s.h_best_cost); cudaFreeHost(s.h_best_mode);
+    cudaFree(s.d_frame); cudaFree(s.d_filt); cudaFree(s.d_cost); cudaFree(s.d_sad); cudaFree(s.d_satd);
+    cudaFree(s.d_best_cost); cudaFree(s.d_best_mode);
+    if (s.ev_start) cudaEventDestroy(s.ev_start);
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slot();
+}
+
+MIPB200_API void mipb200_destroy(mipb200_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    for (auto& s : e->slots) free_slot(s);
+    if (e->aux_stream) { cudaStreamSynchronize(e->aux_stream); cudaStreamDestroy(e->aux_stream); }
+    cudaFree(e->d_aux_filt);
+    delete e;
+}
+
+MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) {
+    if (!out) return fail(MIPB200_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(MIPB200_ENODEV, "no CUDA device: %s (this engine has no CPU fallback)", cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(MIPB200_ENODEV, "device %d not in 0..%d", cfg->device, ndev - 1);
+    CU_TRY(cudaSetDevice(cfg->device));
+    {
+        std::lock_guard<std::mutex> lk(g_init_mutex);
+        if (!g_dev_init[cfg->device]) {
+            const char* ev = getenv("MIPB200_CHUNKS");
+            int chunks = ev ? atoi(ev) : 8;
+            CU_TRY(mipb200::kernels_init(chunks));
+            g_dev_init[cfg->device] = true;
+        }
+    }
+    mipb200_engine* e = new mipb200_engine();
+    e->cfg = *cfg;
+    e->n_ctus = mipb200_num_ctus(cfg->width, cfg->height);
+    e->frame_bytes = (size_t)cfg->width * cfg->height * sizeof(uint16_t);
+    e->cost_bytes = (size_t)e->n_ctus * MIP_COSTS_PER_CTU * sizeof(int32_t);
+    e->cu_bytes4 = (size_t)e->n_ctus * MIP_CUS_PER_CTU * sizeof(int32_t);
+    e->cu_bytes1 = (size_t)e->n_ctus * MIP_CUS_PER_CTU;
+    e->slots.resize(cfg->slots);
+    const bool wc = cfg->emit & MIPB200_EMIT_COSTS, ws = cfg->emit & MIPB200_EMIT_SAD_SATD, wd = cfg->emit & MIPB200_EMIT_DECISIONS;
+#define E_TRY(call)                                                                                     \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            fail(MIPB200_ECUDA, "%s failed: %s", #call, cudaGetErrorString(_e));                        \
+            mipb200_destroy(e);                                                                         \
+            return _e == cudaErrorMemoryAllocation ? MIPB200_ENOMEM : MIPB200_ECUDA;                    \
+        }                                                                                               \
+    } while (0)
+    E_TRY(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+    for (auto& s : e->slots) {
+        E_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        E_TRY(cudaEventCreate(&s.ev_start));
+        E_TRY(cudaEventCreate(&s.ev_k0));
+        E_TRY(cudaEventCreate(&s.ev_k1));
+        E_TRY(cudaEventCreate(&s.ev_done));
+        E_TRY(cudaHostAlloc((void**)&s.h_frame, e->frame_bytes, cudaHostAllocDefault));
+        E_TRY(cudaMalloc((void**)&s.d_frame, e->frame_bytes));
+        if (cfg->filter_type) E_TRY(cudaMalloc((void**)&s.d_filt, e->frame_bytes));
+        E_TRY(cudaMalloc((void**)&s.d_cost, e->cost_bytes));   // always needed (decisions read it)
+        if (wc) E_TRY(cudaHostAlloc((void**)&s.h_cost, e->cost_bytes, cudaHostAllocDefault));
+        if (ws) {
+            E_TRY(cudaMalloc((void**)&s.d_sad, e->cost_bytes));
+            E_TRY(cudaMalloc((void**)&s.d_satd, e->cost_bytes));
+            E_TRY(cudaHostAlloc((void**)&s.h_sad, e->cost_bytes, cudaHostAllocDefault));
+            E_TRY(cudaHostAlloc((void**)&s.h_satd, e->cost_bytes, cudaHostAllocDefault));
+        }
+        if (wd) {
+            E_TRY(cudaMalloc((void**)&s.d_best_mode, e->cu_bytes1));
+            E_TRY(cudaMalloc((void**)&s.d_best_cost, e->cu_bytes4));
+            E_TRY(cudaHostAlloc((void**)&s.h_best_mode, e->cu_bytes1, cudaHostAllocDefault));
+            E_TRY(cudaHostAlloc((void**)&s.h_best_cost, e->cu_bytes4, cudaHostAllocDefault));
+        }
+    }
+#undef E_TRY
+    *out = e;
+    return MIPB200_OK;
+}
+
+MIPB200_API int mipb200_in_flight(const mipb200_engine* e) { return e ? e->in_flight : 0; }
+MIPB200_API long long mipb200_kernel_launches(const mipb200_engine* e) { return e ? e->launches : 0; }
+
+MIPB200_API uint16_t* mipb200_next_input(mipb200_engine* e) {
+    if (!e || e->in_flight >= (int)e->slots.size()) return nullptr;
+    return e->slots[e->head].h_frame;
+}
+
+// filter -> costs -> decisions on `st`; counts launches
+static int enqueue_kernels(mipb200_engine* e, const uint16_t* d_frame, uint16_t* d_filt, int32_t* d_cost, int32_t* d_sad,
+                           int32_t* d_satd, uint8_t* d_bm, int32_t* d_bc, cudaStream_t st) {
+    const mipb200_config& c = e->cfg;
+    const uint16_t* d_ref = d_frame;
+    if (c.filter_type) {
+        CU_TRY(mipb200::launch_filter(d_frame, d_filt, c.width, c.height, c.filter_type, c.kernel_idx, st));
+        e->launches++;
+        d_ref = d_filt;
+    }
+    CU_TRY(mipb200::launch_costs(d_frame, d_ref, c.width, c.height, d_cost, d_sad, d_satd, st));
+    e->launches++;
+    if (d_bm && d_bc) {
+        CU_TRY(mipb200::launch_decide(d_cost, e->n_ctus, d_bm, d_bc, st));
+        e->launches++;
+    }
+    return MIPB200_OK;
+}
+
+MIPB200_API int mipb200_submit(mipb200_engine* e, const uint16_t* frame, int64_t poc) {
+    if (!e || !frame) return fail(MIPB200_EINVAL, "engine or frame is NULL");
+    if (e->in_flight >= (int)e->slots.size()) return fail(MIPB200_EBUSY, "all %d slots in flight; collect first", (int)e->slots.size());
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    Slot& s = e->slots[e->head];
+    if (frame != s.h_frame) memcpy(s.h_frame, frame, e->frame_bytes);
+    s.poc = poc;
+    CU_TRY(cudaEventRecord(s.ev_start, s.stream));
+    CU_TRY(cudaMemcpyAsync(s.d_frame, s.h_frame, e->frame_bytes, cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(cudaEventRecord(s.ev_k0, s.stream));
+    int rc = enqueue_kernels(e, s.d_frame, s.d_filt, s.d_cost, s.d_sad, s.d_satd, s.d_best_mode, s.d_best_cost, s.stream);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(s.ev_k1, s.stream));
+    if (s.h_cost) CU_TRY(cudaMemcpyAsync(s.h_cost, s.d_cost, e->cost_bytes, cudaMemcpyDeviceToHost, s.stream));
+    if (s.h_sad) {
+        CU_TRY(cudaMemcpyAsync(s.h_sad, s.d_sad, e->cost_bytes, cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(cudaMemcpyAsync(s.h_satd, s.d_satd, e->cost_bytes, cudaMemcpyDeviceToHost, s.stream));
+    }
+    if (s.h_best_mode) {
+        CU_TRY(cudaMemcpyAsync(s.h_best_mode, s.d_best_mode, e->cu_bytes1, cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(cudaMemcpyAsync(s.h_best_cost, s.d_best_cost, e->cu_bytes4, cudaMemcpyDeviceToHost, s.stream));
+    }
+    CU_TRY(cudaEventRecord(s.ev_done, s.stream));
+    s.busy = true;
+    e->head = (e->head + 1) % (int)e->slots.size();
+    e->in_flight++;
+    return MIPB200_OK;
+}
+
+MIPB200_API int mipb200_collect(mipb200_engine* e, mipb200_result* out) {
+    if (!e || !out) return fail(MIPB200_EINVAL, "engine or result is NULL");
+    if (e->in_flight == 0) return fail(MIPB200_EEMPTY, "nothing in flight");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    Slot& s = e->slots[e->tail];
+    CU_TRY(cudaEventSynchronize(s.ev_done));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+    out->poc = s.poc;
+    out->n_ctus = e->n_ctus;
+    out->cost = s.h_cost;
+    out->sad = s.h_sad;
+    out->satd = s.h_satd;
+    out->best_mode = s.h_best_mode;
+    out->best_cost = s.h_best_cost;
+    out->gpu_ms = ms;
+    s.busy = false;
+    e->tail = (e->tail + 1) % (int)e->slots.size();
+    e->in_flight--;
+    return MIPB200_OK;
+}
+
+MIPB200_API int mipb200_run_device(mipb200_engine* e, const uint16_t* d_frame, int32_t* d_cost, int32_t* d_sad, int32_t* d_satd,
+                                   uint8_t* d_best_mode, int32_t* d_best_cost, void* stream) {
+    if (!e || !d_frame || !d_cost) return fail(MIPB200_EINVAL, "engine, d_frame and d_cost are required");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
+    if (e->cfg.filter_type && !e->d_aux_filt) CU_TRY(cudaMalloc((void**)&e->d_aux_filt, e->frame_bytes));
+    return enqueue_kernels(e, d_frame, e->d_aux_filt, d_cost, d_sad, d_satd, d_best_mode, d_best_cost, st);
+}
+
+MIPB200_API int mipb200_filter_device(mipb200_engine* e, const uint16_t* d_frame, uint16_t* d_out, void* stream) {
+    if (!e || !d_frame || !d_out) return fail(MIPB200_EINVAL, "engine, d_frame and d_out are required");
+    if (!e->cfg.filter_type) return fail(MIPB200_EINVAL, "engine was created with filter_type 0");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
+    CU_TRY(mipb200::launch_filter(d_frame, d_out, e->cfg.width, e->cfg.height, e->cfg.filter_type, e->cfg.kernel_idx, st));
+    e->launches++;
+    return MIPB200_OK;
+}
+
+MIPB200_API int mipb200_decide_device(mipb200_engine* e, const int32_t* d_cost, uint8_t* d_best_mode, int32_t* d_best_cost, void* stream) {
+    if (!e || !d_cost || !d_best_mode || !d_best_cost) return fail(MIPB200_EINVAL, "NULL argument");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
+    CU_TRY(mipb200::launch_decide(d_cost, e->n_ctus, d_best_mode, d_best_cost, st));
+    e->launches++;
+    return MIPB200_OK;
+}
+
+MIPB200_API int mipb200_sync(mipb200_engine* e) {
+    if (!e) return fail(MIPB200_EINVAL, "engine is NULL");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    for (auto& s : e->slots) CU_TRY(cudaStreamSynchronize(s.stream));
+    CU_TRY(cudaStreamSynchronize(e->aux_stream));
+    return MIPB200_OK;
+}

@@ -1,0 +1,613 @@
+// mip_kernels.cu -- sm_100a kernels of the MIP mode-decision engine.
+//
+// What the reference does in four global-memory-coupled OpenCL kernels
+// (initBoundaries -> MIP_ReducedPred -> upsampleDistortion x3, intra.cl:17-1171, ~1.4 GB of
+// intermediate traffic per 1080p frame) is done here in ONE kernel that never leaves the SM:
+//
+//   CTA  = one (CTU, chunk of the CTU's work).  It stages the 128x128 original samples (as
+//          int32, so a 4-pixel row of a 4x4 block is one LDS.128) and the reference-sample
+//          tile with its top/left halo in shared memory.
+//   lane = one (CU, mode) pair = one output cost.  32 consecutive (CU, mode) pairs of one CU
+//          type form a warp task, so all lanes run the same shape-specialised code, nothing
+//          is reduced across lanes, there is no barrier after staging, and the 32 costs of a
+//          warp leave as one coalesced 128-byte store in the reference's buffer order.
+//   per lane: reduced boundaries (A.2) -> matrix-vector product with IDP.2A on (coef-32)
+//          signed bytes (A.3) into a private shared-memory column -> strip-wise bilinear
+//          up-sampling (A.4) -> per 4x4 block: difference, SAD, Hadamard SATD (A.5).
+//
+// (A.x = arithmetic specification in SURVEY.md Appendix A; file:line = reference repository.)
+#include "mip_kernels.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "mip_filters.h"
+#include "mip_matrices.h"
+#include "mip_tables.h"
+
+namespace mipb200 {
+
+// ------------------------------------------------------------------------------------------
+// Geometry / layout constants
+// ------------------------------------------------------------------------------------------
+constexpr int NT = 512;                 // threads per CTA
+constexpr int NWARPS = NT / 32;
+constexpr int OS = 132;                 // s_orig row stride in int32 words (128 + 4: rows shift 4 banks)
+constexpr int RS = 136;                 // s_ref row stride in uint16 (8 halo/alignment + 128)
+constexpr int REF_ROWS = 129;           // rows -1..127
+constexpr int RED_WORDS = 32;           // packed reduced-prediction words per thread (64 samples)
+
+constexpr int M2_OFF = 0, M2_STRIDE = 520;            // 6 x (64 x 8 B), +8 B pad against bank aliasing
+constexpr int M1_OFF = M2_OFF + 6 * M2_STRIDE, M1_STRIDE = 136;   // 8 x (16 x 8 B) + 8
+constexpr int M0_OFF = M1_OFF + 8 * M1_STRIDE, M0_STRIDE = 68;    // 16 x (16 x 4 B) + 4
+constexpr int MAT_BYTES = M0_OFF + 16 * M0_STRIDE;    // 5296
+
+constexpr int SM_ORIG = 0;
+constexpr int SM_ORIG_BYTES = 128 * OS * 4;                    // 67584
+constexpr int SM_REF = SM_ORIG + SM_ORIG_BYTES;
+constexpr int SM_REF_BYTES = REF_ROWS * RS * 2;                // 35088
+constexpr int SM_RED = SM_REF + SM_REF_BYTES;
+constexpr int SM_RED_BYTES = RED_WORDS * NT * 4;               // 65536
+constexpr int SM_MAT = SM_RED + SM_RED_BYTES;
+constexpr int SM_MISC = SM_MAT + ((MAT_BYTES + 15) / 16) * 16; // s_dc, work counter
+constexpr int SM_TOTAL = SM_MISC + 16;
+
+constexpr int MAX_CHUNKS = 64;
+constexpr int MAX_WORK = 3200;          // warp tasks per CTU (3058 used)
+
+struct DevType {
+    uint8_t w, h, cols, rows, size_id, modes, shape, pad;
+    uint16_t n, nwt;       // CUs per CTU, warp tasks per CTU
+    uint32_t cost_off, cu_off;
+    uint8_t xs[32], ys[32];
+};
+
+__constant__ DevType c_types[MIP_NUM_TYPES];
+__constant__ uint32_t c_work[MAX_WORK];        // type | (warp task index inside the type) << 8
+__constant__ int c_chunk_begin[MAX_CHUNKS + 1];
+__device__ uint8_t g_mat[MAT_BYTES];           // (coef - 32) as signed bytes, padded layout above
+
+static int g_chunks = 0;
+
+// the 17 distinct CU shapes
+enum Shape {
+    S64x64, S32x32, S32x16, S16x32, S32x8, S8x32, S16x16, S16x8, S8x16,  // sizeId 2
+    S32x4, S4x32, S16x4, S4x16, S8x8, S8x4, S4x8,                        // sizeId 1
+    S4x4,                                                                // sizeId 0
+    NUM_SHAPES
+};
+
+static int shape_of(int w, int h) {
+    static const int tab[NUM_SHAPES][2] = {{64, 64}, {32, 32}, {32, 16}, {16, 32}, {32, 8}, {8, 32}, {16, 16}, {16, 8}, {8, 16},
+                                           {32, 4},  {4, 32},  {16, 4},  {4, 16},  {8, 8},  {8, 4},  {4, 8},   {4, 4}};
+    for (int i = 0; i < NUM_SHAPES; ++i)
+        if (tab[i][0] == w && tab[i][1] == h) return i;
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Device helpers
+// ------------------------------------------------------------------------------------------
+struct Ctx {
+    const int* s_orig;        // [128][OS]
+    const uint16_t* s_ref0;   // element (0,0) of the reference tile; (y,x) at y*RS + x, y,x >= -1
+    const uint16_t* s_dc;     // one cell holding 512
+    uint32_t* s_red;          // this thread's column of the [RED_WORDS][NT] scratch
+    const uint8_t* s_mat;
+    int ctuX, ctuY;
+};
+
+__device__ __forceinline__ int ilog2c(int v) { return v == 1 ? 0 : v == 2 ? 1 : v == 4 ? 2 : v == 8 ? 3 : v == 16 ? 4 : 5; }
+
+// 4x4 SATD of kernel_aux_functions.cl:142-249.  d = orig - pred in raster order.
+// The last butterfly stage is folded into |a+b| + |a-b| = 2*max(|a|,|b|); the DC pair keeps
+// its explicit form because of the mean-scaled DC term (abs(d0) >> 2).
+__device__ __forceinline__ int satd4x4(const int (&d)[16]) {
+    int m[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int a0 = d[i] + d[12 + i], a1 = d[4 + i] + d[8 + i];
+        int a2 = d[4 + i] - d[8 + i], a3 = d[i] - d[12 + i];
+        m[i] = a0 + a1; m[4 + i] = a2 + a3; m[8 + i] = a0 - a1; m[12 + i] = a3 - a2;
+    }
+    int s2 = 0;  // sum of max(|.|,|.|) over the 7 non-DC pairs
+    int dc_pair = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int b0 = m[4 * r] + m[4 * r + 3], b1 = m[4 * r + 1] + m[4 * r + 2];
+        int b2 = m[4 * r + 1] - m[4 * r + 2], b3 = m[4 * r] - m[4 * r + 3];
+        if (r == 0) dc_pair = abs(b0 - b1) + (abs(b0 + b1) >> 2);
+        else s2 += max(abs(b0), abs(b1));
+        s2 += max(abs(b2), abs(b3));
+    }
+    return (2 * s2 + dc_pair + 1) >> 1;
+}
+
+// One 4x4 block: p = predicted samples (raster), o = pointer to the block's first original
+// sample in s_orig.  Accumulates SAD and SATD.
+__device__ __forceinline__ void block_cost(const int (&p)[16], const int* o, int& sad, int& satd) {
+    int d[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int4 v = *reinterpret_cast<const int4*>(o + i * OS);
+        d[4 * i + 0] = v.x - p[4 * i + 0];
+        d[4 * i + 1] = v.y - p[4 * i + 1];
+        d[4 * i + 2] = v.z - p[4 * i + 2];
+        d[4 * i + 3] = v.w - p[4 * i + 3];
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sad += abs(d[k]);
+    satd += satd4x4(d);
+}
+
+// reduced-prediction sample (j, c) of this thread's scratch column (R samples per row)
+template <int R>
+__device__ __forceinline__ int red_at(const uint32_t* s_red, int j, int c) {
+    const int idx = j * R + c;
+    return reinterpret_cast<const uint16_t*>(s_red + (idx >> 1) * NT)[idx & 1];
+}
+
+// Horizontal up-sampling (A.4, intra.cl:818-844) of reduced row j for the four columns of
+// strip s (x0 = 4s).  Lval = refL[y] of that row (used only where x < UH).
+template <int R, int UH>
+__device__ __forceinline__ void hor_row(const uint32_t* s_red, int j, int s, int Lval, int (&cur)[4]) {
+    if constexpr (UH == 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cur[k] = red_at<R>(s_red, j, 4 * s + k);
+    } else if constexpr (UH == 2) {
+        const int a0 = red_at<R>(s_red, j, 2 * s), a1 = red_at<R>(s_red, j, 2 * s + 1);
+        const int bef = (s == 0) ? Lval : red_at<R>(s_red, j, 2 * s - 1);
+        cur[0] = (bef + a0 + 1) >> 1; cur[1] = a0; cur[2] = (a0 + a1 + 1) >> 1; cur[3] = a1;
+    } else if constexpr (UH == 4) {
+        const int a = red_at<R>(s_red, j, s);
+        const int bef = (s == 0) ? Lval : red_at<R>(s_red, j, s - 1);
+        const int dl = a - bef, v = 4 * bef + 2;
+        cur[0] = (v + dl) >> 2; cur[1] = (v + 2 * dl) >> 2; cur[2] = (v + 3 * dl) >> 2; cur[3] = a;
+    } else {  // UH == 8: two strips per reduced column
+        const int c = s >> 1;
+        const int a = red_at<R>(s_red, j, c);
+        const int bef = (c == 0) ? Lval : red_at<R>(s_red, j, c - 1);
+        const int dl = a - bef, v = 8 * bef + 4 + (s & 1) * 4 * dl;
+        cur[0] = (v + dl) >> 3; cur[1] = (v + 2 * dl) >> 3; cur[2] = (v + 3 * dl) >> 3; cur[3] = (v + 4 * dl) >> 3;
+    }
+}
+
+// One (CU, mode): everything from the boundaries to SAD/SATD.  SID = sizeId, W x H = CU size.
+template <int SID, int W, int H>
+__device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mode, int& sad, int& satd) {
+    constexpr int R = SID == 2 ? 8 : 4;                   // reduced prediction side
+    constexpr int B = SID == 0 ? 2 : 4;                   // reduced boundary samples per side
+    constexpr int M = SID == 2 ? 6 : (SID == 1 ? 8 : 16); // matrices
+    constexpr int UH = W / R, UV = H / R;
+
+    // ---- A.1 complete boundaries: pointer + stride into the reference tile (intra.cl:96-107, 232-243)
+    const int absX = c.ctuX + cuX, absY = c.ctuY + cuY;
+    const uint16_t *T, *L;
+    int stT, stL;
+    if (absY > 0) { T = c.s_ref0 + (cuY - 1) * RS + cuX; stT = 1; }
+    else if (absX == 0) { T = c.s_dc; stT = 0; }
+    else { T = c.s_ref0 + cuX - 1; stT = 0; }                 // F[0][X-1] replicated
+    if (absX > 0) { L = c.s_ref0 + cuY * RS + cuX - 1; stL = RS; }
+    else if (absY == 0) { L = c.s_dc; stL = 0; }
+    else { L = c.s_ref0 + (cuY - 1) * RS; stL = 0; }          // F[Y-1][0] replicated
+
+    // ---- A.2 reduced boundaries (intra.cl:127-141, 260-279)
+    constexpr int DT = W / B, DL = H / B;
+    int bd[2 * B];
+    {
+        int redT[B], redL[B];
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+            int sT = 0, sL = 0;
+#pragma unroll
+            for (int t = 0; t < DT; ++t) sT += T[(q * DT + t) * stT];
+#pragma unroll
+            for (int t = 0; t < DL; ++t) sL += L[(q * DL + t) * stL];
+            redT[q] = (sT + (DT >> 1)) >> ilog2c(DT);
+            redL[q] = (sL + (DL >> 1)) >> ilog2c(DL);
+        }
+        const bool tr = mode >= M;
+#pragma unroll
+        for (int i = 0; i < B; ++i) { bd[i] = tr ? redL[i] : redT[i]; bd[B + i] = tr ? redT[i] : redL[i]; }
+    }
+    // ---- A.3 input vector, packed s16x2 for IDP.2A (intra.cl:434-452)
+    const bool tr = mode >= M;
+    const int mat = tr ? mode - M : mode;
+    const int first = bd[0];
+    int ipk[B];
+    {
+        int in[2 * B];
+        in[0] = (SID == 2) ? 0 : 512 - first;
+#pragma unroll
+        for (int i = 1; i < 2 * B; ++i) in[i] = bd[i] - first;
+#pragma unroll
+        for (int k = 0; k < B; ++k) ipk[k] = (in[2 * k] & 0xffff) | (in[2 * k + 1] << 16);
+    }
+    // matrix row p of output position (a, b): p = a*R + b, or b*R + a for transposed modes
+    const int stepB = tr ? R : 1, stepA = tr ? 1 : R;
+
+    if constexpr (SID == 0) {
+        // 4x4: the reduced prediction is the prediction (intra.cl:726-727, 934-935)
+        const uint8_t* mb = c.s_mat + M0_OFF + mat * M0_STRIDE;
+        int p[16];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int cw = *reinterpret_cast<const int*>(mb + (a * stepA + b * stepB) * 4);
+                int acc = 32;
+                acc = __dp2a_lo(ipk[0], cw, acc);
+                acc = __dp2a_hi(ipk[1], cw, acc);
+                p[a * 4 + b] = min(max((acc >> 6) + first, 0), 1023);
+            }
+        block_cost(p, c.s_orig + cuY * OS + cuX, sad, satd);
+        return;
+    } else {
+        // ---- A.3 matrix-vector product -> private scratch column, two samples per word
+        const uint8_t* mb = c.s_mat + (SID == 2 ? M2_OFF + mat * M2_STRIDE : M1_OFF + mat * M1_STRIDE);
+#pragma unroll 1
+        for (int a = 0; a < R; ++a) {
+#pragma unroll
+            for (int b = 0; b < R; b += 2) {
+                int v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int2 cw = *reinterpret_cast<const int2*>(mb + (a * stepA + (b + e) * stepB) * 8);
+                    int acc = 32;
+                    acc = __dp2a_lo(ipk[0], cw.x, acc);
+                    acc = __dp2a_hi(ipk[1], cw.x, acc);
+                    acc = __dp2a_lo(ipk[2], cw.y, acc);
+                    acc = __dp2a_hi(ipk[3], cw.y, acc);
+                    v[e] = min(max((acc >> 6) + first, 0), 1023);
+                }
+                c.s_red[((a * R + b) >> 1) * NT] = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
+            }
+        }
+        // ---- A.4 + A.5 strip-wise: 4 columns at a time, top to bottom
+        const int* orig = c.s_orig + cuY * OS + cuX;
+#pragma unroll 1
+        for (int s = 0; s < W / 4; ++s) {
+            const int x0 = 4 * s;
+            int prev[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) prev[k] = T[(x0 + k) * stT];
+            if constexpr (UV >= 4) {
+#pragma unroll 1
+                for (int j = 0; j < R; ++j) {
+                    int cur[4];
+                    hor_row<R, UH>(c.s_red, j, s, (int)L[(j * UV + UV - 1) * stL], cur);
+                    int dl[4], v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { dl[k] = cur[k] - prev[k]; v[k] = UV * prev[k] + (UV >> 1); }
+#pragma unroll
+                    for (int blk = 0; blk < UV / 4; ++blk) {
+                        int p[16];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (blk * 4 + i == UV - 1) p[4 * i + k] = cur[k];
+                                else { v[k] += dl[k]; p[4 * i + k] = v[k] >> ilog2c(UV); }
+                            }
+                        block_cost(p, orig + (j * UV + blk * 4) * OS + x0, sad, satd);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) prev[k] = cur[k];
+                }
+            } else if constexpr (UV == 2) {
+#pragma unroll 1
+                for (int jp = 0; jp < R / 2; ++jp) {
+                    int c0[4], c1[4], p[16];
+                    hor_row<R, UH>(c.s_red, 2 * jp, s, (int)L[(4 * jp + 1) * stL], c0);
+                    hor_row<R, UH>(c.s_red, 2 * jp + 1, s, (int)L[(4 * jp + 3) * stL], c1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        p[k] = (prev[k] + c0[k] + 1) >> 1;
+                        p[4 + k] = c0[k];
+                        p[8 + k] = (c0[k] + c1[k] + 1) >> 1;
+                        p[12 + k] = c1[k];
+                        prev[k] = c1[k];
+                    }
+                    block_cost(p, orig + (4 * jp) * OS + x0, sad, satd);
+                }
+            } else {  // UV == 1: reduced rows are pixel rows
+#pragma unroll 1
+                for (int jq = 0; jq < R / 4; ++jq) {
+                    int p[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        int cur[4];
+                        hor_row<R, UH>(c.s_red, 4 * jq + i, s, (int)L[(4 * jq + i) * stL], cur);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) p[4 * i + k] = cur[k];
+                    }
+                    block_cost(p, orig + (4 * jq) * OS + x0, sad, satd);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// The fused kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1)
+mip_cost_kernel(const uint16_t* __restrict__ g_orig, const uint16_t* __restrict__ g_ref, int W, int H,
+                int chunks, int32_t* __restrict__ g_cost, int32_t* __restrict__ g_sad, int32_t* __restrict__ g_satd) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int* s_orig = reinterpret_cast<int*>(smem + SM_ORIG);
+    uint16_t* s_ref = reinterpret_cast<uint16_t*>(smem + SM_REF);
+    uint32_t* s_red = reinterpret_cast<uint32_t*>(smem + SM_RED);
+    uint8_t* s_mat = smem + SM_MAT;
+    uint16_t* s_dc = reinterpret_cast<uint16_t*>(smem + SM_MISC);
+    int* s_next = reinterpret_cast<int*>(smem + SM_MISC + 4);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ctu = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    const int ctuCols = W >> 7;
+    const int ctuX = (ctu % ctuCols) << 7, ctuY = (ctu / ctuCols) << 7;
+    const int rowsValid = min(128, H - ctuY);
+
+    // ---- stage: originals as int32, 8 pixels per thread per step (coalesced 16-byte loads)
+    for (int i = tid; i < 128 * 16; i += NT) {
+        const int y = i >> 4, xc = (i & 15) << 3;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (y < rowsValid) v = __ldg(reinterpret_cast<const uint4*>(g_orig + (size_t)(ctuY + y) * W + ctuX + xc));
+        int4* dst = reinterpret_cast<int4*>(s_orig + y * OS + xc);
+        dst[0] = make_int4(v.x & 0xffff, v.x >> 16, v.y & 0xffff, v.y >> 16);
+        dst[1] = make_int4(v.z & 0xffff, v.z >> 16, v.w & 0xffff, v.w >> 16);
+    }
+    // ---- stage: reference tile rows -1..127, columns -8..127 (column -1 is the left halo)
+    for (int i = tid; i < REF_ROWS * 17; i += NT) {
+        const int r = i / 17, xc = (i % 17) * 8 - 8;
+        const int y = ctuY + r - 1, x = ctuX + xc;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (y >= 0 && y < H && x >= 0) v = __ldg(reinterpret_cast<const uint4*>(g_ref + (size_t)y * W + x));
+        *reinterpret_cast<uint4*>(s_ref + r * RS + xc + 8) = v;
+    }
+    for (int i = tid; i < MAT_BYTES / 4; i += NT)
+        reinterpret_cast<uint32_t*>(s_mat)[i] = reinterpret_cast<const uint32_t*>(g_mat)[i];
+    if (tid == 0) { *s_dc = 512; *s_next = 0; }
+    __syncthreads();
+
+    Ctx c;
+    c.s_orig = s_orig;
+    c.s_ref0 = s_ref + RS + 8;
+    c.s_dc = s_dc;
+    c.s_red = s_red + tid;
+    c.s_mat = s_mat;
+    c.ctuX = ctuX;
+    c.ctuY = ctuY;
+
+    const int wbeg = c_chunk_begin[chunk], wcnt = c_chunk_begin[chunk + 1] - wbeg;
+    const size_t ctuBase = (size_t)ctu * MIP_COSTS_PER_CTU;
+
+    while (true) {
+        int wi = 0;
+        if (lane == 0) wi = atomicAdd(s_next, 1);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (wi >= wcnt) break;
+        const uint32_t rec = c_work[wbeg + wi];
+        const int t = rec & 0xff, wt = rec >> 8;
+        const DevType& ty = c_types[t];
+        const int modes = ty.modes, ntask = ty.n * modes;
+        const int task = wt * 32 + lane;
+        const bool inRange = task < ntask;
+        const int tcl = inRange ? task : ntask - 1;
+        const int cu = tcl / modes, mode = tcl - cu * modes;
+        const int cuX = ty.xs[cu % ty.cols], cuY = ty.ys[cu / ty.cols];
+        const bool active = inRange && (ctuY + cuY + ty.h <= H);
+        int sad = 0, satd = 0;
+        if (__any_sync(0xffffffffu, active)) {
+            switch (ty.shape) {
+                case S64x64: run_task<2, 64, 64>(c, cuX, cuY, mode, sad, satd); break;
+                case S32x32: run_task<2, 32, 32>(c, cuX, cuY, mode, sad, satd); break;
+                case S32x16: run_task<2, 32, 16>(c, cuX, cuY, mode, sad, satd); break;
+                case S16x32: run_task<2, 16, 32>(c, cuX, cuY, mode, sad, satd); break;
+                case S32x8:  run_task<2, 32, 8>(c, cuX, cuY, mode, sad, satd); break;
+                case S8x32:  run_task<2, 8, 32>(c, cuX, cuY, mode, sad, satd); break;
+                case S16x16: run_task<2, 16, 16>(c, cuX, cuY, mode, sad, satd); break;
+                case S16x8:  run_task<2, 16, 8>(c, cuX, cuY, mode, sad, satd); break;
+                case S8x16:  run_task<2, 8, 16>(c, cuX, cuY, mode, sad, satd); break;
+                case S32x4:  run_task<1, 32, 4>(c, cuX, cuY, mode, sad, satd); break;
+                case S4x32:  run_task<1, 4, 32>(c, cuX, cuY, mode, sad, satd); break;
+                case S16x4:  run_task<1, 16, 4>(c, cuX, cuY, mode, sad, satd); break;
+                case S4x16:  run_task<1, 4, 16>(c, cuX, cuY, mode, sad, satd); break;
+                case S8x8:   run_task<1, 8, 8>(c, cuX, cuY, mode, sad, satd); break;
+                case S8x4:   run_task<1, 8, 4>(c, cuX, cuY, mode, sad, satd); break;
+                case S4x8:   run_task<1, 4, 8>(c, cuX, cuY, mode, sad, satd); break;
+                default:     run_task<0, 4, 4>(c, cuX, cuY, mode, sad, satd); break;
+            }
+        }
+        if (inRange) {
+            const size_t o = ctuBase + ty.cost_off + task;
+            g_cost[o] = active ? min(2 * sad, satd) : -1;   // intra.cl:1166
+            if (g_sad) g_sad[o] = active ? sad : -1;
+            if (g_satd) g_satd[o] = active ? satd : -1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Low-pass filters for alternative samples (A.6; intra.cl:1639-3823).  One thread per pixel.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int px_or_zero(const uint16_t* f, int W, int H, int x, int y) {
+    return (x >= 0 && x < W && y >= 0 && y < H) ? (int)__ldg(f + (size_t)y * W + x) : 0;
+}
+
+template <int RAD, bool IS2D>
+__global__ void __launch_bounds__(256)
+mip_filter_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int W, int H, int kidx) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    int num = 0, den = 0;
+    if constexpr (IS2D) {
+        // numerator and denominator over the in-frame taps (intra.cl:2993-3011, 3215-3235)
+#pragma unroll
+        for (int dy = -RAD; dy <= RAD; ++dy)
+#pragma unroll
+            for (int dx = -RAD; dx <= RAD; ++dx) {
+                const int xx = x + dx, yy = y + dy;
+                if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+                const int k = RAD == 1 ? mip_k3(kidx, dy, dx) : mip_k5(kidx, dy, dx);
+                num += k * (int)__ldg(in + (size_t)yy * W + xx);
+                den += k;
+            }
+    } else {
+        // separable passes with the first row of the table; denominator by position class
+        int k[2 * RAD + 1];
+#pragma unroll
+        for (int i = 0; i <= 2 * RAD; ++i) k[i] = RAD == 1 ? mip_k3(kidx, -1, i - 1) : mip_k5(kidx, -2, i - 2);
+#pragma unroll
+        for (int dy = -RAD; dy <= RAD; ++dy) {
+            int hor = 0;
+#pragma unroll
+            for (int dx = -RAD; dx <= RAD; ++dx) hor += k[dx + RAD] * px_or_zero(in, W, H, x + dx, y + dy);
+            num += k[dy + RAD] * hor;
+        }
+        if constexpr (RAD == 1) {  // intra.cl:3281-3285, 3437-3458
+            const int nEdges = (x == 0) + (x == W - 1) + (y == 0) + (y == H - 1);
+            const int k0 = k[0], k1 = k[1];
+            den = nEdges >= 2 ? (k0 + 2 * k1 + k1 * k1) : (nEdges == 1 ? (2 * k0 + 3 * k1 + k1 * k1) : (4 * k0 + 4 * k1 + k1 * k1));
+        } else {                   // intra.cl:3523-3551, 3753-3786
+            auto ksum = [&](int i0, int j0) {
+                int s = 0;
+                for (int i = i0; i < 5; ++i)
+                    for (int j = j0; j < 5; ++j) s += mip_k5(kidx, i - 2, j - 2);
+                return s;
+            };
+            const bool oTB = (y == 0) || (y == H - 1), iTB = (y == 1) || (y == H - 2);
+            const bool oLR = (x == 0) || (x == W - 1), iLR = (x == 1) || (x == W - 2);
+            const bool oC = oTB && oLR, iC = iTB && iLR;
+            const bool ifc = (oLR && iTB) || (iLR && oTB);
+            const bool oE = !oC && !ifc && (oTB || oLR), iE = !iC && !ifc && (iTB || iLR);
+            den = ksum(0, 0);
+#pragma unroll
+            for (int dy = -2; dy <= 2; ++dy)
+                if (y + dy < 0 || y + dy >= H) den -= k[dy + 2];
+            if (oC) den = ksum(2, 2);
+            if (iC) den = ksum(1, 1);
+            if (oE) den = ksum(0, 2);
+            if (iE) den = ksum(0, 1);
+            if (ifc) den = ksum(1, 2);
+        }
+    }
+    out[(size_t)y * W + x] = (uint16_t)((num + den / 2) / den);
+}
+
+// ------------------------------------------------------------------------------------------
+// Decisions: per CU argmin over its modes (lowest mode wins ties; skipped CUs -> 0xFF / -1)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mip_decide_kernel(const int32_t* __restrict__ cost, int n_ctus, uint8_t* __restrict__ best_mode,
+                  int32_t* __restrict__ best_cost) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_ctus * MIP_CUS_PER_CTU) return;
+    const int ctu = idx / MIP_CUS_PER_CTU, k = idx - ctu * MIP_CUS_PER_CTU;
+    int lo = 0, hi = MIP_NUM_TYPES - 1;   // last type with cu_off <= k
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)c_types[mid].cu_off <= k) lo = mid; else hi = mid - 1;
+    }
+    const DevType& ty = c_types[lo];
+    const int modes = ty.modes;
+    const int32_t* c = cost + (size_t)ctu * MIP_COSTS_PER_CTU + ty.cost_off + (k - ty.cu_off) * modes;
+    int bm = 0xFF, bc = -1;
+    if (c[0] != -1) {
+        bm = 0; bc = c[0];
+        for (int m = 1; m < modes; ++m) {
+            const int v = c[m];
+            if (v < bc) { bc = v; bm = m; }
+        }
+    }
+    best_mode[idx] = (uint8_t)bm;
+    best_cost[idx] = bc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+cudaError_t kernels_init(int chunks) {
+    if (chunks < 1) chunks = 1;
+    if (chunks > MAX_CHUNKS) chunks = MAX_CHUNKS;
+    cudaError_t err;
+    // CU tables
+    DevType types[MIP_NUM_TYPES];
+    memset(types, 0, sizeof(types));
+    std::vector<uint32_t> work;
+    std::vector<double> wcost;
+    for (int t = 0; t < MIP_NUM_TYPES; ++t) {
+        const mip_cu_type_t& s = MIP_TYPES[t];
+        DevType& d = types[t];
+        d.w = s.w; d.h = s.h; d.cols = s.cols; d.rows = s.rows; d.size_id = s.size_id; d.modes = s.modes;
+        d.shape = (uint8_t)shape_of(s.w, s.h);
+        d.n = s.n; d.nwt = (uint16_t)((s.n * s.modes + 31) / 32);
+        d.cost_off = s.cost_off; d.cu_off = s.cu_off;
+        memcpy(d.xs, s.xs, 32); memcpy(d.ys, s.ys, 32);
+        const double mv = s.size_id == 2 ? 700.0 : (s.size_id == 1 ? 200.0 : 120.0);
+        const double c = mv + 11.0 * s.w * s.h + 2.0 * (s.w + s.h) + 60.0;
+        for (int w = 0; w < d.nwt; ++w) { work.push_back((uint32_t)t | ((uint32_t)w << 8)); wcost.push_back(c); }
+    }
+    if ((int)work.size() > MAX_WORK) return cudaErrorInvalidValue;
+    // contiguous, cost-balanced partition of the work list into `chunks` chunks
+    int begin[MAX_CHUNKS + 1];
+    double total = 0;
+    for (double c : wcost) total += c;
+    begin[0] = 0;
+    double acc = 0;
+    int k = 1;
+    for (size_t i = 0; i < work.size() && k < chunks; ++i) {
+        acc += wcost[i];
+        if (acc >= total * k / chunks) begin[k++] = (int)i + 1;
+    }
+    while (k <= chunks) begin[k++] = (int)work.size();
+    work.resize(MAX_WORK, 0);
+    if ((err = cudaMemcpyToSymbol(c_types, types, sizeof(types))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_work, work.data(), sizeof(uint32_t) * MAX_WORK)) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_chunk_begin, begin, sizeof(int) * (chunks + 1))) != cudaSuccess) return err;
+    // matrices: (coef - 32) as signed bytes in the padded shared-memory layout
+    std::vector<uint8_t> mat(MAT_BYTES, 0);
+    for (int m = 0; m < 6; ++m)
+        for (int p = 0; p < 64; ++p)
+            for (int i = 0; i < 8; ++i) mat[M2_OFF + m * M2_STRIDE + p * 8 + i] = (uint8_t)(int8_t)((int)MIP_MAT_ID2[m][p][i] - 32);
+    for (int m = 0; m < 8; ++m)
+        for (int p = 0; p < 16; ++p)
+            for (int i = 0; i < 8; ++i) mat[M1_OFF + m * M1_STRIDE + p * 8 + i] = (uint8_t)(int8_t)((int)MIP_MAT_ID1[m][p][i] - 32);
+    for (int m = 0; m < 16; ++m)
+        for (int p = 0; p < 16; ++p)
+            for (int i = 0; i < 4; ++i) mat[M0_OFF + m * M0_STRIDE + p * 4 + i] = (uint8_t)(int8_t)((int)MIP_MAT_ID0[m][p][i] - 32);
+    if ((err = cudaMemcpyToSymbol(g_mat, mat.data(), MAT_BYTES)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(mip_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)) != cudaSuccess) return err;
+    g_chunks = chunks;
+    return cudaSuccess;
+}
+
+int kernels_chunks_per_ctu() { return g_chunks; }
+
+cudaError_t launch_costs(const uint16_t* d_orig, const uint16_t* d_ref, int W, int H, int32_t* d_cost, int32_t* d_sad,
+                         int32_t* d_satd, cudaStream_t st) {
+    const int nctu = (W >> 7) * ((H + 127) >> 7);
+    mip_cost_kernel<<<nctu * g_chunks, NT, SM_TOTAL, st>>>(d_orig, d_ref, W, H, g_chunks, d_cost, d_sad, d_satd);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_filter(const uint16_t* d_in, uint16_t* d_out, int W, int H, int ft, int kidx, cudaStream_t st) {
+    dim3 grid((W + 31) / 32, (H + 7) / 8), block(256);
+    const bool is5 = ft >= 5, is2d = (ft == 3 || ft == 4 || ft == 7 || ft == 8);
+    if (is2d && !is5) mip_filter_kernel<1, true><<<grid, block, 0, st>>>(d_in, d_out, W, H, kidx);
+    else if (is2d) mip_filter_kernel<2, true><<<grid, block, 0, st>>>(d_in, d_out, W, H, kidx);
+    else if (!is5) mip_filter_kernel<1, false><<<grid, block, 0, st>>>(d_in, d_out, W, H, kidx);
+    else mip_filter_kernel<2, false><<<grid, block, 0, st>>>(d_in, d_out, W, H, kidx);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decide(const int32_t* d_cost, int n_ctus, uint8_t* d_best_mode, int32_t* d_best_cost, cudaStream_t st) {
+    const int n = n_ctus * MIP_CUS_PER_CTU;
+    mip_decide_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_cost, n_ctus, d_best_mode, d_best_cost);
+    return cudaGetLastError();
+}
+
+}  // namespace mipb200
