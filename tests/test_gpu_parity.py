@@ -59,8 +59,10 @@ def test_filter_only(mip, oracle, ft):
         with mip.Engine(256, 88, filter_type=ft, kernel_idx=kidx, slots=1) as eng:
             d_in = torch.from_numpy(f.view(np.int16)).cuda()
             d_out = torch.empty_like(d_in)
-            eng.filter_device(d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
+            st = torch.cuda.Stream()
+            eng.filter_device(d_in.data_ptr(), d_out.data_ptr(), st.cuda_stream)
+            st.synchronize()
             got = d_out.cpu().numpy().view(np.uint16)
         _assert_same(got, oracle.filter_frame(f, ft, kidx), f"filter ft={ft} kidx={kidx}")
 
@@ -95,9 +97,11 @@ def test_device_resident_path(mip, oracle):
         d_bm = torch.empty((eng.n_ctus, mip.CUS_PER_CTU), dtype=torch.uint8, device="cuda")
         d_bc = torch.empty((eng.n_ctus, mip.CUS_PER_CTU), dtype=torch.int32, device="cuda")
         n0 = eng.kernel_launches()
-        eng.run_device(d_in.data_ptr(), d_cost.data_ptr(), d_best_mode=d_bm.data_ptr(), d_best_cost=d_bc.data_ptr(),
-                       stream=torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
+        st = torch.cuda.Stream()
+        eng.run_device(d_in.data_ptr(), d_cost.data_ptr(), d_best_mode=d_bm.data_ptr(), d_best_cost=d_bc.data_ptr(),
+                       stream=st.cuda_stream)
+        st.synchronize()                      # the work ran on the stream we passed, nowhere else
         assert eng.kernel_launches() - n0 == 2
         want = oracle.run_frame(f)
         _assert_same(d_cost.cpu().numpy(), want, "device cost")
