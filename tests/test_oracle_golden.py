@@ -75,7 +75,8 @@ def test_kat_per_type_sums(kat_runs):
     assert got == KAT["per_type_sum_cost_orig_ctu3"]
 
 
-OCL = sorted(glob.glob(os.path.join(GOLD, "ocl_b200_*.npz")))
+OCL = sorted(glob.glob(os.path.join(GOLD, "ocl_b200_cost_*.npz")))
+OCL_FILT = sorted(glob.glob(os.path.join(GOLD, "ocl_b200_filters_*.npz")))
 
 
 @pytest.mark.skipif(not OCL, reason="no reference-OpenCL-on-B200 fixtures committed yet")
@@ -99,3 +100,19 @@ def frames_from_fixture(z):
     w, h, seed = int(z["width"]), int(z["height"]), int(z["seed"])
     return {"kat": lambda: frames.kat_frame(w, h), "noise": lambda: frames.noise_frame(w, h, seed),
             "natural": lambda: frames.natural_frame(w, h, seed)}[kind]()
+
+
+@pytest.mark.skipif(not OCL_FILT, reason="no reference-OpenCL-on-B200 filter fixtures committed yet")
+@pytest.mark.parametrize("path", OCL_FILT, ids=os.path.basename)
+def test_oracle_filters_equal_reference_opencl_kernels_on_b200(oracle, path):
+    """All 8 filterFrame_* kernels x every KernelIdx, run unmodified on the B200 == oracle, every pixel."""
+    z = np.load(path)
+    frame = frames_from_fixture(z)
+    n = 0
+    for ft in range(1, 9):
+        for kidx in range(T.num_kernel_idx(ft)):
+            want = z[f"f{ft}k{kidx}"]
+            got = oracle.filter_frame(frame, ft, kidx)
+            assert np.array_equal(got, want), f"filter_type={ft} kernel_idx={kidx}: {int((got != want).sum())} pixels differ"
+            n += 1
+    assert n == 32
