@@ -52,6 +52,22 @@ OP_KERNEL(mix_fadd_imad_lop3, asm volatile("add.f32 %0, %0, %1;" : "+r"(r[c]) : 
 OP_KERNEL(mix_dp2a_lop3, asm volatile("dp2a.lo.s32.s32 %0, %1, %2, %0;" : "+r"(r[c]) : "r"(b), "r"(d)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(b), "r"(d)))
 OP_KERNEL(mix_viadd16_imad, asm volatile("add.s16x2 %0, %0, %1;" : "+r"(r[c]) : "r"(b)); asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(r[c]) : "r"(b), "r"(d)))
 
+// which pipe does an op share? pair it with IMAD (fma pipe) and with LOP3 (alu pipe)
+#define IMAD_ asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(r[c]) : "r"(b), "r"(d))
+#define LOP3_ asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(b), "r"(d))
+OP_KERNEL(mix_sad_imad, asm volatile("sad.s32 %0, %1, %2, %0;" : "+r"(r[c]) : "r"(b), "r"(d)); IMAD_)
+OP_KERNEL(mix_sad_lop3, asm volatile("sad.s32 %0, %1, %2, %0;" : "+r"(r[c]) : "r"(b), "r"(d)); LOP3_)
+OP_KERNEL(mix_abs_imad, asm volatile("abs.s32 %0, %0;" : "+r"(r[c])); IMAD_)
+OP_KERNEL(mix_abs_lop3, asm volatile("abs.s32 %0, %0;" : "+r"(r[c])); LOP3_)
+OP_KERNEL(mix_shf_imad, asm volatile("shf.r.wrap.b32 %0, %0, %1, 5;" : "+r"(r[c]) : "r"(b)); IMAD_)
+OP_KERNEL(mix_dp2a_imad, asm volatile("dp2a.lo.s32.s32 %0, %1, %2, %0;" : "+r"(r[c]) : "r"(b), "r"(d)); IMAD_)
+OP_KERNEL(mix_viadd16_lop3, asm volatile("add.s16x2 %0, %0, %1;" : "+r"(r[c]) : "r"(b)); LOP3_)
+OP_KERNEL(mix_vmax16_imad, asm volatile("max.s16x2 %0, %0, %1;" : "+r"(r[c]) : "r"(b)); asm volatile("min.s16x2 %0, %0, %1;" : "+r"(r[c]) : "r"(d)); IMAD_)
+OP_KERNEL(mix_max_imad, asm volatile("max.s32 %0, %0, %1;" : "+r"(r[c]) : "r"(b)); asm volatile("min.s32 %0, %0, %1;" : "+r"(r[c]) : "r"(d)); IMAD_)
+OP_KERNEL(mix_prmt_imad, asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(r[c]) : "r"(b)); IMAD_)
+OP_KERNEL(mix_lea_imad, r[c] = b + (r[c] >> 3); IMAD_)
+OP_KERNEL(mix_lea_lop3, r[c] = b + (r[c] >> 3); LOP3_)
+
 typedef void (*kern_t)(int*, int, int);
 
 static double run(kern_t k, int ops_per_body, int sms, int* d_out, const char* name, FILE* js, bool last) {
@@ -96,7 +112,10 @@ int main(int argc, char** argv) {
     RUN(viadd16x2, 1, false); RUN(vimnmx16x2, 1, false); RUN(prmt, 1, false);
     RUN(fadd, 1, false); RUN(ffma, 1, false); RUN(fabsadd, 1, false); RUN(hadd2, 1, false);
     RUN(mix_imad_iadd3, 2, false); RUN(mix_ffma_lop3, 2, false); RUN(mix_fadd_imad, 2, false);
-    RUN(mix_fadd_imad_lop3, 3, false); RUN(mix_dp2a_lop3, 2, false); RUN(mix_viadd16_imad, 2, true);
+    RUN(mix_fadd_imad_lop3, 3, false); RUN(mix_dp2a_lop3, 2, false); RUN(mix_viadd16_imad, 2, false);
+    RUN(mix_sad_imad, 2, false); RUN(mix_sad_lop3, 2, false); RUN(mix_abs_imad, 2, false); RUN(mix_abs_lop3, 2, false);
+    RUN(mix_shf_imad, 2, false); RUN(mix_dp2a_imad, 2, false); RUN(mix_viadd16_lop3, 2, false); RUN(mix_vmax16_imad, 3, false);
+    RUN(mix_max_imad, 3, false); RUN(mix_prmt_imad, 2, false); RUN(mix_lea_imad, 2, false); RUN(mix_lea_lop3, 2, true);
     fprintf(js, "}\n");
     fclose(js);
     return 0;

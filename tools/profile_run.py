@@ -19,15 +19,24 @@ pool = torch.from_numpy(np.stack([frames.natural_frame(W, H, i) for i in range(2
 cost = torch.empty((eng.n_ctus, mipb200.COSTS_PER_CTU), dtype=torch.int32, device="cuda")
 bm = torch.empty((eng.n_ctus, mipb200.CUS_PER_CTU), dtype=torch.uint8, device="cuda")
 bc = torch.empty((eng.n_ctus, mipb200.CUS_PER_CTU), dtype=torch.int32, device="cuda")
-stream = torch.cuda.Stream()
-torch.cuda.set_stream(stream)
-st = stream.cuda_stream
+ns = int(os.environ.get("STREAMS", "1"))   # frames round-robin over this many streams (independent frames overlap)
+streams = [torch.cuda.Stream() for _ in range(ns)]
+engs = [eng] + [mipb200.Engine(W, H, filter_type=8, kernel_idx=2, slots=1, emit=mipb200.EMIT_COSTS | mipb200.EMIT_DECISIONS) for _ in range(ns - 1)]
+outs = [(cost, bm, bc)] + [(torch.empty_like(cost), torch.empty_like(bm), torch.empty_like(bc)) for _ in range(ns - 1)]
+torch.cuda.set_stream(streams[0])
 torch.cuda.synchronize()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for i in range(n + 1):
-    if i == 1:
-        ev0.record()
-    eng.run_device(pool[i % 2].data_ptr(), cost.data_ptr(), d_best_mode=bm.data_ptr(), d_best_cost=bc.data_ptr(), stream=st)
-ev1.record()
+for i in range(n + ns):
+    if i == ns:
+        torch.cuda.synchronize()
+        ev0.record(streams[0])
+        for s_ in streams[1:]:
+            s_.wait_stream(streams[0])
+    k = i % ns
+    c_, m_, b_ = outs[k]
+    engs[k].run_device(pool[i % 2].data_ptr(), c_.data_ptr(), d_best_mode=m_.data_ptr(), d_best_cost=b_.data_ptr(), stream=streams[k].cuda_stream)
+for s_ in streams[1:]:
+    streams[0].wait_stream(s_)
+ev1.record(streams[0])
 torch.cuda.synchronize()
-print(f"{n} frames {W}x{H}: {ev0.elapsed_time(ev1) / n:.3f} ms/frame, checksum {int(cost.to(torch.int64).clamp(min=0).sum())}")
+print(f"{n} frames {W}x{H} on {ns} stream(s): {ev0.elapsed_time(ev1) / n:.3f} ms/frame, checksum {int(cost.to(torch.int64).clamp(min=0).sum())}")

@@ -125,7 +125,7 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
         std::lock_guard<std::mutex> lk(g_init_mutex);
         if (!g_dev_init[cfg->device]) {
             const char* ev = getenv("MIPB200_CHUNKS");
-            int chunks = ev ? atoi(ev) : 8;
+            int chunks = ev ? atoi(ev) : 4;   // chunks per CTU half
             CU_TRY(mipb200::kernels_init(chunks));
             g_dev_init[cfg->device] = true;
         }

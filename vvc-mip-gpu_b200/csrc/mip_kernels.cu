@@ -4,9 +4,10 @@
 // (initBoundaries -> MIP_ReducedPred -> upsampleDistortion x3, intra.cl:17-1171, ~1.4 GB of
 // intermediate traffic per 1080p frame) is done here in ONE kernel that never leaves the SM:
 //
-//   CTA  = one (CTU, chunk of the CTU's work).  It stages the 128x128 original samples (as
-//          int32, so a 4-pixel row of a 4x4 block is one LDS.128) and the reference-sample
-//          tile with its top/left halo in shared memory.
+//   CTA  = one (CTU half, chunk of that half's work).  No CU crosses the y = 64 line of its CTU, so
+//          the top and bottom 128x64 halves are independent.  The CTA stages the half's original
+//          samples (as int32 holding o+1, so a 4-pixel row of a 4x4 block is one LDS.128) and the
+//          reference-sample tile with its top/left halo in shared memory; two CTAs share an SM.
 //   lane = one (CU, mode) pair = one output cost.  32 consecutive (CU, mode) pairs of one CU
 //          type form a warp task, so all lanes run the same shape-specialised code, nothing
 //          is reduced across lanes, there is no barrier after staging, and the 32 costs of a
@@ -19,6 +20,7 @@
 #include "mip_kernels.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -33,11 +35,15 @@ namespace mipb200 {
 // ------------------------------------------------------------------------------------------
 // Geometry / layout constants
 // ------------------------------------------------------------------------------------------
-constexpr int NT = 512;                 // threads per CTA
+#ifndef MIP_NT
+#define MIP_NT 384
+#endif
+constexpr int NT = MIP_NT;              // threads per CTA
 constexpr int NWARPS = NT / 32;
 constexpr int OS = 132;                 // s_orig row stride in int32 words (128 + 4: rows shift 4 banks)
 constexpr int RS = 136;                 // s_ref row stride in uint16 (8 halo/alignment + 128)
-constexpr int REF_ROWS = 129;           // rows -1..127
+constexpr int TILE_ROWS = 64;            // a CTA works on the top or bottom half of a CTU
+constexpr int REF_ROWS = TILE_ROWS + 1;  // rows -1..63
 constexpr int RED_WORDS = 32;           // packed reduced-prediction words per thread (64 samples)
 
 constexpr int M2_OFF = 0, M2_STRIDE = 520;            // 6 x (64 x 8 B), +8 B pad against bank aliasing
@@ -46,28 +52,31 @@ constexpr int M0_OFF = M1_OFF + 8 * M1_STRIDE, M0_STRIDE = 68;    // 16 x (16 x 
 constexpr int MAT_BYTES = M0_OFF + 16 * M0_STRIDE;    // 5296
 
 constexpr int SM_ORIG = 0;
-constexpr int SM_ORIG_BYTES = 128 * OS * 4;                    // 67584
+constexpr int SM_ORIG_BYTES = TILE_ROWS * OS * 4;              // 33792
 constexpr int SM_REF = SM_ORIG + SM_ORIG_BYTES;
-constexpr int SM_REF_BYTES = REF_ROWS * RS * 2;                // 35088
+constexpr int SM_REF_BYTES = REF_ROWS * RS * 2;                // 17680
 constexpr int SM_RED = SM_REF + SM_REF_BYTES;
-constexpr int SM_RED_BYTES = RED_WORDS * NT * 4;               // 65536
+constexpr int SM_RED_BYTES = RED_WORDS * NT * 4;               // 49152 at NT = 384
 constexpr int SM_MAT = SM_RED + SM_RED_BYTES;
 constexpr int SM_MISC = SM_MAT + ((MAT_BYTES + 15) / 16) * 16; // s_dc, work counter
 constexpr int SM_TOTAL = SM_MISC + 16;
 
 constexpr int MAX_CHUNKS = 64;
-constexpr int MAX_WORK = 3200;          // warp tasks per CTU (3058 used)
+constexpr int MAX_WORK = 1700;          // warp tasks per CTU half
 
 struct DevType {
-    uint8_t w, h, cols, rows, size_id, modes, shape, pad;
+    uint8_t w, h, cols, rows, size_id, modes, shape, cols_log2;
     uint16_t n, nwt;       // CUs per CTU, warp tasks per CTU
+    uint32_t mode_magic;   // task / modes == (task * mode_magic) >> 16 for every task of the type
+    uint16_t first_cu[2], n_cu[2];   // CUs of the type that lie in the top / bottom half of the CTU (contiguous in CU order)
+    uint8_t parts_log2, pad[3];      // lanes that share one (CU, mode): 4 for 64x64 (a quarter of the strips each), else 1
     uint32_t cost_off, cu_off;
     uint8_t xs[32], ys[32];
 };
 
 __constant__ DevType c_types[MIP_NUM_TYPES];
-__constant__ uint32_t c_work[MAX_WORK];        // type | (warp task index inside the type) << 8
-__constant__ int c_chunk_begin[MAX_CHUNKS + 1];
+__constant__ uint32_t c_work[2][MAX_WORK];     // per half: type | (warp task index inside the type's half) << 8
+__constant__ int c_chunk_begin[2][MAX_CHUNKS + 1];
 __device__ uint8_t g_mat[MAT_BYTES];           // (coef - 32) as signed bytes, padded layout above
 
 static int g_chunks = 0;
@@ -92,19 +101,20 @@ static int shape_of(int w, int h) {
 // Device helpers
 // ------------------------------------------------------------------------------------------
 struct Ctx {
-    const int* s_orig;        // [128][OS]
+    const int* s_orig;        // [128][OS], holds orig + 1
     const uint16_t* s_ref0;   // element (0,0) of the reference tile; (y,x) at y*RS + x, y,x >= -1
     const uint16_t* s_dc;     // one cell holding 512
     uint32_t* s_red;          // this thread's column of the [RED_WORDS][NT] scratch
     const uint8_t* s_mat;
-    int ctuX, ctuY;
+    int ctuX, tileY;          // frame position of the tile origin
 };
 
 __device__ __forceinline__ int ilog2c(int v) { return v == 1 ? 0 : v == 2 ? 1 : v == 4 ? 2 : v == 8 ? 3 : v == 16 ? 4 : 5; }
 
 // 4x4 SATD of kernel_aux_functions.cl:142-249.  d = orig - pred in raster order.
-// The last butterfly stage is folded into |a+b| + |a-b| = 2*max(|a|,|b|); the DC pair keeps
-// its explicit form because of the mean-scaled DC term (abs(d0) >> 2).
+// Three butterfly stages are explicit; the fourth is folded into the absolute sums:
+// |a + b| + |a - b| = |a - (-b)| + |a - b| = two VABSDIFF (abs-diff-accumulate) on (a, -b) and (a, b).
+// The DC pair is split because of the mean-scaled DC term (abs(d0) >> 2, :244-245).
 __device__ __forceinline__ int satd4x4(const int (&d)[16]) {
     int m[16];
 #pragma unroll
@@ -113,34 +123,37 @@ __device__ __forceinline__ int satd4x4(const int (&d)[16]) {
         int a2 = d[4 + i] - d[8 + i], a3 = d[i] - d[12 + i];
         m[i] = a0 + a1; m[4 + i] = a2 + a3; m[8 + i] = a0 - a1; m[12 + i] = a3 - a2;
     }
-    int s2 = 0;  // sum of max(|.|,|.|) over the 7 non-DC pairs
-    int dc_pair = 0;
+    int s = 0, dc = 0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        int b0 = m[4 * r] + m[4 * r + 3], b1 = m[4 * r + 1] + m[4 * r + 2];
-        int b2 = m[4 * r + 1] - m[4 * r + 2], b3 = m[4 * r] - m[4 * r + 3];
-        if (r == 0) dc_pair = abs(b0 - b1) + (abs(b0 + b1) >> 2);
-        else s2 += max(abs(b0), abs(b1));
-        s2 += max(abs(b2), abs(b3));
+        const int b0 = m[4 * r] + m[4 * r + 3], b1 = m[4 * r + 1] + m[4 * r + 2];
+        const int b2 = m[4 * r + 1] - m[4 * r + 2], b3 = m[4 * r] - m[4 * r + 3];
+        if (r == 0) dc = __sad(b0, -b1, 0);          // |b0 + b1| = |coefficient 0|
+        else s = __sad(b0, -b1, s);
+        s = __sad(b0, b1, s);
+        s = __sad(b3, -b2, s);
+        s = __sad(b3, b2, s);
     }
-    return (2 * s2 + dc_pair + 1) >> 1;
+    return (s + (dc >> 2) + 1) >> 1;
 }
 
-// One 4x4 block: p = predicted samples (raster), o = pointer to the block's first original
-// sample in s_orig.  Accumulates SAD and SATD.
-__device__ __forceinline__ void block_cost(const int (&p)[16], const int* o, int& sad, int& satd) {
-    int d[16];
+// The original-sample tile holds o + 1, so that the difference against an interpolated sample
+// floor(v / 2^s) costs one LEA.HI:  o - (v >> s) = (o + 1) + (~v >> s)   (two's complement).
+// A difference against a sample p that needs no shift is (o + 1) + ~p.
+__device__ __forceinline__ int diff_shifted(int o1, int nv, int s) { return o1 + (nv >> s); }
+__device__ __forceinline__ int diff_plain(int o1, int p) { return o1 + ~p; }
+
+// One 4x4 block given its 16 differences d = orig - pred (raster): SAD += sum|d| (one VABSDIFF
+// each), SATD += satd4x4(d).
+__device__ __forceinline__ void block_cost_d(const int (&d)[16], int& sad, int& satd) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int4 v = *reinterpret_cast<const int4*>(o + i * OS);
-        d[4 * i + 0] = v.x - p[4 * i + 0];
-        d[4 * i + 1] = v.y - p[4 * i + 1];
-        d[4 * i + 2] = v.z - p[4 * i + 2];
-        d[4 * i + 3] = v.w - p[4 * i + 3];
-    }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) sad += abs(d[k]);
+    for (int k = 0; k < 16; ++k) sad = __sad(d[k], 0, sad);
     satd += satd4x4(d);
+}
+
+__device__ __forceinline__ void load_o1_row(const int* o, int (&v)[4]) {
+    const int4 t = *reinterpret_cast<const int4*>(o);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
 
 // reduced-prediction sample (j, c) of this thread's scratch column (R samples per row)
@@ -152,6 +165,12 @@ __device__ __forceinline__ int red_at(const uint32_t* s_red, int j, int c) {
 
 // Horizontal up-sampling (A.4, intra.cl:818-844) of reduced row j for the four columns of
 // strip s (x0 = 4s).  Lval = refL[y] of that row (used only where x < UH).
+__device__ __forceinline__ int avg_up(int a, int b) {   // (a + b + 1) >> 1 as IADD3 + SHF
+    int t;
+    asm("add.s32 %0, %1, %2;" : "=r"(t) : "r"(a), "r"(b));
+    return (t + 1) >> 1;
+}
+
 template <int R, int UH>
 __device__ __forceinline__ void hor_row(const uint32_t* s_red, int j, int s, int Lval, int (&cur)[4]) {
     if constexpr (UH == 1) {
@@ -160,7 +179,7 @@ __device__ __forceinline__ void hor_row(const uint32_t* s_red, int j, int s, int
     } else if constexpr (UH == 2) {
         const int a0 = red_at<R>(s_red, j, 2 * s), a1 = red_at<R>(s_red, j, 2 * s + 1);
         const int bef = (s == 0) ? Lval : red_at<R>(s_red, j, 2 * s - 1);
-        cur[0] = (bef + a0 + 1) >> 1; cur[1] = a0; cur[2] = (a0 + a1 + 1) >> 1; cur[3] = a1;
+        cur[0] = avg_up(bef, a0); cur[1] = a0; cur[2] = avg_up(a0, a1); cur[3] = a1;
     } else if constexpr (UH == 4) {
         const int a = red_at<R>(s_red, j, s);
         const int bef = (s == 0) ? Lval : red_at<R>(s_red, j, s - 1);
@@ -176,15 +195,17 @@ __device__ __forceinline__ void hor_row(const uint32_t* s_red, int j, int s, int
 }
 
 // One (CU, mode): everything from the boundaries to SAD/SATD.  SID = sizeId, W x H = CU size.
-template <int SID, int W, int H>
-__device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mode, int& sad, int& satd) {
+// cuX, cuY are relative to the tile.  PARTS lanes share the (CU, mode): lane `part` takes a contiguous
+// 1/PARTS of the strips (every lane still computes the whole reduced prediction into its own scratch).
+template <int SID, int W, int H, int PARTS = 1>
+__device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mode, int part, int& sad, int& satd) {
     constexpr int R = SID == 2 ? 8 : 4;                   // reduced prediction side
     constexpr int B = SID == 0 ? 2 : 4;                   // reduced boundary samples per side
     constexpr int M = SID == 2 ? 6 : (SID == 1 ? 8 : 16); // matrices
     constexpr int UH = W / R, UV = H / R;
 
     // ---- A.1 complete boundaries: pointer + stride into the reference tile (intra.cl:96-107, 232-243)
-    const int absX = c.ctuX + cuX, absY = c.ctuY + cuY;
+    const int absX = c.ctuX + cuX, absY = c.tileY + cuY;
     const uint16_t *T, *L;
     int stT, stL;
     if (absY > 0) { T = c.s_ref0 + (cuY - 1) * RS + cuX; stT = 1; }
@@ -243,7 +264,15 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
                 acc = __dp2a_hi(ipk[1], cw, acc);
                 p[a * 4 + b] = min(max((acc >> 6) + first, 0), 1023);
             }
-        block_cost(p, c.s_orig + cuY * OS + cuX, sad, satd);
+        int d[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int o1[4];
+            load_o1_row(c.s_orig + (cuY + i) * OS + cuX, o1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d[4 * i + k] = diff_plain(o1[k], p[4 * i + k]);
+        }
+        block_cost_d(d, sad, satd);
         return;
     } else {
         // ---- A.3 matrix-vector product -> private scratch column, two samples per word
@@ -268,63 +297,75 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
         }
         // ---- A.4 + A.5 strip-wise: 4 columns at a time, top to bottom
         const int* orig = c.s_orig + cuY * OS + cuX;
+        constexpr int STRIPS = W / 4 / PARTS;
 #pragma unroll 1
-        for (int s = 0; s < W / 4; ++s) {
+        for (int s = part * STRIPS; s < (part + 1) * STRIPS; ++s) {
             const int x0 = 4 * s;
             int prev[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) prev[k] = T[(x0 + k) * stT];
             if constexpr (UV >= 4) {
-#pragma unroll 1
+                constexpr int SH = UV == 4 ? 2 : 3;
+#pragma unroll 2
                 for (int j = 0; j < R; ++j) {
                     int cur[4];
                     hor_row<R, UH>(c.s_red, j, s, (int)L[(j * UV + UV - 1) * stL], cur);
-                    int dl[4], v[4];
+                    // nv = ~(UV*prev + UV/2 + i*dl) walks down the rows; see diff_shifted()
+                    int dl[4], nv[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { dl[k] = cur[k] - prev[k]; v[k] = UV * prev[k] + (UV >> 1); }
+                    for (int k = 0; k < 4; ++k) { dl[k] = prev[k] - cur[k]; nv[k] = -UV * prev[k] - ((UV >> 1) + 1); }
 #pragma unroll
                     for (int blk = 0; blk < UV / 4; ++blk) {
-                        int p[16];
+                        int d[16];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
+                        for (int i = 0; i < 4; ++i) {
+                            int o1[4];
+                            load_o1_row(orig + (j * UV + blk * 4 + i) * OS + x0, o1);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                if (blk * 4 + i == UV - 1) p[4 * i + k] = cur[k];
-                                else { v[k] += dl[k]; p[4 * i + k] = v[k] >> ilog2c(UV); }
+                                if (blk * 4 + i == UV - 1) d[4 * i + k] = diff_plain(o1[k], cur[k]);
+                                else { nv[k] += dl[k]; d[4 * i + k] = diff_shifted(o1[k], nv[k], SH); }
                             }
-                        block_cost(p, orig + (j * UV + blk * 4) * OS + x0, sad, satd);
+                        }
+                        block_cost_d(d, sad, satd);
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) prev[k] = cur[k];
                 }
             } else if constexpr (UV == 2) {
-#pragma unroll 1
+#pragma unroll 2
                 for (int jp = 0; jp < R / 2; ++jp) {
-                    int c0[4], c1[4], p[16];
+                    int c0[4], c1[4], d[16], o1[4];
                     hor_row<R, UH>(c.s_red, 2 * jp, s, (int)L[(4 * jp + 1) * stL], c0);
                     hor_row<R, UH>(c.s_red, 2 * jp + 1, s, (int)L[(4 * jp + 3) * stL], c1);
+                    const int* o = orig + (4 * jp) * OS + x0;
+                    load_o1_row(o, o1);            // row 0: (prev + c0 + 1) >> 1
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        p[k] = (prev[k] + c0[k] + 1) >> 1;
-                        p[4 + k] = c0[k];
-                        p[8 + k] = (c0[k] + c1[k] + 1) >> 1;
-                        p[12 + k] = c1[k];
-                        prev[k] = c1[k];
-                    }
-                    block_cost(p, orig + (4 * jp) * OS + x0, sad, satd);
+                    for (int k = 0; k < 4; ++k) d[k] = diff_shifted(o1[k], -prev[k] - c0[k] - 2, 1);
+                    load_o1_row(o + OS, o1);       // row 1: c0
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) d[4 + k] = diff_plain(o1[k], c0[k]);
+                    load_o1_row(o + 2 * OS, o1);   // row 2: (c0 + c1 + 1) >> 1
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) d[8 + k] = diff_shifted(o1[k], -c0[k] - c1[k] - 2, 1);
+                    load_o1_row(o + 3 * OS, o1);   // row 3: c1
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { d[12 + k] = diff_plain(o1[k], c1[k]); prev[k] = c1[k]; }
+                    block_cost_d(d, sad, satd);
                 }
             } else {  // UV == 1: reduced rows are pixel rows
 #pragma unroll 1
                 for (int jq = 0; jq < R / 4; ++jq) {
-                    int p[16];
+                    int d[16];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        int cur[4];
+                        int cur[4], o1[4];
                         hor_row<R, UH>(c.s_red, 4 * jq + i, s, (int)L[(4 * jq + i) * stL], cur);
+                        load_o1_row(orig + (4 * jq + i) * OS + x0, o1);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) p[4 * i + k] = cur[k];
+                        for (int k = 0; k < 4; ++k) d[4 * i + k] = diff_plain(o1[k], cur[k]);
                     }
-                    block_cost(p, orig + (4 * jq) * OS + x0, sad, satd);
+                    block_cost_d(d, sad, satd);
                 }
             }
         }
@@ -334,7 +375,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 // ------------------------------------------------------------------------------------------
 // The fused kernel
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 2)
 mip_cost_kernel(const uint16_t* __restrict__ g_orig, const uint16_t* __restrict__ g_ref, int W, int H,
                 int chunks, int32_t* __restrict__ g_cost, int32_t* __restrict__ g_sad, int32_t* __restrict__ g_satd) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -346,30 +387,38 @@ mip_cost_kernel(const uint16_t* __restrict__ g_orig, const uint16_t* __restrict_
     int* s_next = reinterpret_cast<int*>(smem + SM_MISC + 4);
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int ctu = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    // chunk-major unit order: CTAs that are resident together work on the same chunk (the same CU
+    // shapes, hence the same code) of different CTU halves, which keeps the instruction caches warm
     const int ctuCols = W >> 7;
-    const int ctuX = (ctu % ctuCols) << 7, ctuY = (ctu / ctuCols) << 7;
-    const int rowsValid = min(128, H - ctuY);
+    const int halves = 2 * ctuCols * ((H + 127) >> 7);
+    const int chunk = blockIdx.x / halves, hu = blockIdx.x - chunk * halves;
+    const int ctu = hu >> 1, half = hu & 1;
+    const int ctuX = (ctu % ctuCols) << 7, tileY = ((ctu / ctuCols) << 7) + half * TILE_ROWS;
+    const int rowsValid = min(TILE_ROWS, H - tileY);     // <= 0: the whole half lies below the frame
+    const int wbeg = c_chunk_begin[half][chunk], wcnt = c_chunk_begin[half][chunk + 1] - wbeg;
+    const size_t ctuBase = (size_t)ctu * MIP_COSTS_PER_CTU;
 
-    // ---- stage: originals as int32, 8 pixels per thread per step (coalesced 16-byte loads)
-    for (int i = tid; i < 128 * 16; i += NT) {
-        const int y = i >> 4, xc = (i & 15) << 3;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (y < rowsValid) v = __ldg(reinterpret_cast<const uint4*>(g_orig + (size_t)(ctuY + y) * W + ctuX + xc));
-        int4* dst = reinterpret_cast<int4*>(s_orig + y * OS + xc);
-        dst[0] = make_int4(v.x & 0xffff, v.x >> 16, v.y & 0xffff, v.y >> 16);
-        dst[1] = make_int4(v.z & 0xffff, v.z >> 16, v.w & 0xffff, v.w >> 16);
+    if (rowsValid > 0) {
+        // ---- stage: originals (+1) as int32, 8 pixels per thread per step (coalesced 16-byte loads)
+        for (int i = tid; i < TILE_ROWS * 16; i += NT) {
+            const int y = i >> 4, xc = (i & 15) << 3;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (y < rowsValid) v = __ldg(reinterpret_cast<const uint4*>(g_orig + (size_t)(tileY + y) * W + ctuX + xc));
+            int4* dst = reinterpret_cast<int4*>(s_orig + y * OS + xc);
+            dst[0] = make_int4((v.x & 0xffff) + 1, (v.x >> 16) + 1, (v.y & 0xffff) + 1, (v.y >> 16) + 1);   // o + 1, see diff_shifted()
+            dst[1] = make_int4((v.z & 0xffff) + 1, (v.z >> 16) + 1, (v.w & 0xffff) + 1, (v.w >> 16) + 1);
+        }
+        // ---- stage: reference tile rows -1..63, columns -8..127 (column -1 is the left halo)
+        for (int i = tid; i < REF_ROWS * 17; i += NT) {
+            const int r = i / 17, xc = (i % 17) * 8 - 8;
+            const int y = tileY + r - 1, x = ctuX + xc;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (y >= 0 && y < H && x >= 0) v = __ldg(reinterpret_cast<const uint4*>(g_ref + (size_t)y * W + x));
+            *reinterpret_cast<uint4*>(s_ref + r * RS + xc + 8) = v;
+        }
+        for (int i = tid; i < MAT_BYTES / 4; i += NT)
+            reinterpret_cast<uint32_t*>(s_mat)[i] = reinterpret_cast<const uint32_t*>(g_mat)[i];
     }
-    // ---- stage: reference tile rows -1..127, columns -8..127 (column -1 is the left halo)
-    for (int i = tid; i < REF_ROWS * 17; i += NT) {
-        const int r = i / 17, xc = (i % 17) * 8 - 8;
-        const int y = ctuY + r - 1, x = ctuX + xc;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (y >= 0 && y < H && x >= 0) v = __ldg(reinterpret_cast<const uint4*>(g_ref + (size_t)y * W + x));
-        *reinterpret_cast<uint4*>(s_ref + r * RS + xc + 8) = v;
-    }
-    for (int i = tid; i < MAT_BYTES / 4; i += NT)
-        reinterpret_cast<uint32_t*>(s_mat)[i] = reinterpret_cast<const uint32_t*>(g_mat)[i];
     if (tid == 0) { *s_dc = 512; *s_next = 0; }
     __syncthreads();
 
@@ -380,50 +429,54 @@ mip_cost_kernel(const uint16_t* __restrict__ g_orig, const uint16_t* __restrict_
     c.s_red = s_red + tid;
     c.s_mat = s_mat;
     c.ctuX = ctuX;
-    c.ctuY = ctuY;
-
-    const int wbeg = c_chunk_begin[chunk], wcnt = c_chunk_begin[chunk + 1] - wbeg;
-    const size_t ctuBase = (size_t)ctu * MIP_COSTS_PER_CTU;
+    c.tileY = tileY;
 
     while (true) {
         int wi = 0;
         if (lane == 0) wi = atomicAdd(s_next, 1);
         wi = __shfl_sync(0xffffffffu, wi, 0);
         if (wi >= wcnt) break;
-        const uint32_t rec = c_work[wbeg + wi];
+        const uint32_t rec = c_work[half][wbeg + wi];
         const int t = rec & 0xff, wt = rec >> 8;
         const DevType& ty = c_types[t];
-        const int modes = ty.modes, ntask = ty.n * modes;
+        const int modes = ty.modes, pl2 = ty.parts_log2;
+        const int ntask = (ty.n_cu[half] * modes) << pl2;
         const int task = wt * 32 + lane;
         const bool inRange = task < ntask;
         const int tcl = inRange ? task : ntask - 1;
-        const int cu = tcl / modes, mode = tcl - cu * modes;
-        const int cuX = ty.xs[cu % ty.cols], cuY = ty.ys[cu / ty.cols];
-        const bool active = inRange && (ctuY + cuY + ty.h <= H);
+        const int part = tcl & ((1 << pl2) - 1), cm = tcl >> pl2;
+        const int cuLocal = (int)(((uint32_t)cm * ty.mode_magic) >> 16), mode = cm - cuLocal * modes;
+        const int cu = ty.first_cu[half] + cuLocal;
+        const int cuX = ty.xs[cu & (ty.cols - 1)], cuY = ty.ys[cu >> ty.cols_log2] - half * TILE_ROWS;
+        const bool active = inRange && (cuY + ty.h <= rowsValid);
         int sad = 0, satd = 0;
         if (__any_sync(0xffffffffu, active)) {
             switch (ty.shape) {
-                case S64x64: run_task<2, 64, 64>(c, cuX, cuY, mode, sad, satd); break;
-                case S32x32: run_task<2, 32, 32>(c, cuX, cuY, mode, sad, satd); break;
-                case S32x16: run_task<2, 32, 16>(c, cuX, cuY, mode, sad, satd); break;
-                case S16x32: run_task<2, 16, 32>(c, cuX, cuY, mode, sad, satd); break;
-                case S32x8:  run_task<2, 32, 8>(c, cuX, cuY, mode, sad, satd); break;
-                case S8x32:  run_task<2, 8, 32>(c, cuX, cuY, mode, sad, satd); break;
-                case S16x16: run_task<2, 16, 16>(c, cuX, cuY, mode, sad, satd); break;
-                case S16x8:  run_task<2, 16, 8>(c, cuX, cuY, mode, sad, satd); break;
-                case S8x16:  run_task<2, 8, 16>(c, cuX, cuY, mode, sad, satd); break;
-                case S32x4:  run_task<1, 32, 4>(c, cuX, cuY, mode, sad, satd); break;
-                case S4x32:  run_task<1, 4, 32>(c, cuX, cuY, mode, sad, satd); break;
-                case S16x4:  run_task<1, 16, 4>(c, cuX, cuY, mode, sad, satd); break;
-                case S4x16:  run_task<1, 4, 16>(c, cuX, cuY, mode, sad, satd); break;
-                case S8x8:   run_task<1, 8, 8>(c, cuX, cuY, mode, sad, satd); break;
-                case S8x4:   run_task<1, 8, 4>(c, cuX, cuY, mode, sad, satd); break;
-                case S4x8:   run_task<1, 4, 8>(c, cuX, cuY, mode, sad, satd); break;
-                default:     run_task<0, 4, 4>(c, cuX, cuY, mode, sad, satd); break;
+                case S64x64: run_task<2, 64, 64, 4>(c, cuX, cuY, mode, part, sad, satd); break;
+                case S32x32: run_task<2, 32, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S32x16: run_task<2, 32, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S16x32: run_task<2, 16, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S32x8:  run_task<2, 32, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S8x32:  run_task<2, 8, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S16x16: run_task<2, 16, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S16x8:  run_task<2, 16, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S8x16:  run_task<2, 8, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S32x4:  run_task<1, 32, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S4x32:  run_task<1, 4, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S16x4:  run_task<1, 16, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S4x16:  run_task<1, 4, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S8x8:   run_task<1, 8, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S8x4:   run_task<1, 8, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S4x8:   run_task<1, 4, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
+                default:     run_task<0, 4, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
+            }
+            if (pl2) {   // lanes 4k..4k+3 hold the four strip groups of one (CU, mode)
+                sad += __shfl_xor_sync(0xffffffffu, sad, 1);  satd += __shfl_xor_sync(0xffffffffu, satd, 1);
+                sad += __shfl_xor_sync(0xffffffffu, sad, 2);  satd += __shfl_xor_sync(0xffffffffu, satd, 2);
             }
         }
-        if (inRange) {
-            const size_t o = ctuBase + ty.cost_off + task;
+        if (inRange && part == 0) {
+            const size_t o = ctuBase + ty.cost_off + cu * modes + mode;
             g_cost[o] = active ? min(2 * sad, satd) : -1;   // intra.cl:1166
             if (g_sad) g_sad[o] = active ? sad : -1;
             if (g_satd) g_satd[o] = active ? satd : -1;
@@ -537,37 +590,60 @@ cudaError_t kernels_init(int chunks) {
     // CU tables
     DevType types[MIP_NUM_TYPES];
     memset(types, 0, sizeof(types));
-    std::vector<uint32_t> work;
-    std::vector<double> wcost;
+    std::vector<uint32_t> work[2];
+    std::vector<double> wcost[2];
     for (int t = 0; t < MIP_NUM_TYPES; ++t) {
         const mip_cu_type_t& s = MIP_TYPES[t];
         DevType& d = types[t];
         d.w = s.w; d.h = s.h; d.cols = s.cols; d.rows = s.rows; d.size_id = s.size_id; d.modes = s.modes;
         d.shape = (uint8_t)shape_of(s.w, s.h);
         d.n = s.n; d.nwt = (uint16_t)((s.n * s.modes + 31) / 32);
+        d.cols_log2 = 0;
+        while ((1 << d.cols_log2) < s.cols) d.cols_log2++;
+        if ((1 << d.cols_log2) != s.cols) return cudaErrorInvalidValue;   // every CU grid has a power-of-two column count
+        d.mode_magic = (65536u + s.modes - 1) / s.modes;
+        for (int task = 0; task < s.n * s.modes; ++task)
+            if ((int)(((uint32_t)task * d.mode_magic) >> 16) != task / s.modes) return cudaErrorInvalidValue;
         d.cost_off = s.cost_off; d.cu_off = s.cu_off;
         memcpy(d.xs, s.xs, 32); memcpy(d.ys, s.ys, 32);
-        const double mv = s.size_id == 2 ? 700.0 : (s.size_id == 1 ? 200.0 : 120.0);
-        const double c = mv + 11.0 * s.w * s.h + 2.0 * (s.w + s.h) + 60.0;
-        for (int w = 0; w < d.nwt; ++w) { work.push_back((uint32_t)t | ((uint32_t)w << 8)); wcost.push_back(c); }
+        d.parts_log2 = (s.w == 64 && s.h == 64) ? 2 : 0;
+        // CUs per CTU half: CU order is raster, so each half is one contiguous run; no CU crosses y = 64
+        for (int hf = 0; hf < 2; ++hf) {
+            int first = -1, cnt = 0;
+            for (int cu = 0; cu < s.n; ++cu) {
+                const int y = s.ys[cu / s.cols];
+                if (y / 64 != (y + s.h - 1) / 64) return cudaErrorInvalidValue;
+                if (y / 64 == hf) { if (first < 0) first = cu; else if (cu != first + cnt) return cudaErrorInvalidValue; cnt++; }
+            }
+            d.first_cu[hf] = (uint16_t)(first < 0 ? 0 : first);
+            d.n_cu[hf] = (uint16_t)cnt;
+            const double mv = s.size_id == 2 ? 700.0 : (s.size_id == 1 ? 200.0 : 120.0);
+            const double c = (mv + 11.0 * s.w * s.h + 2.0 * (s.w + s.h) + 60.0) / (1 << d.parts_log2) + (d.parts_log2 ? mv : 0.0);
+            const int nw = ((cnt * s.modes << d.parts_log2) + 31) / 32;
+            for (int w = 0; w < nw; ++w) { work[hf].push_back((uint32_t)t | ((uint32_t)w << 8)); wcost[hf].push_back(c); }
+        }
     }
-    if ((int)work.size() > MAX_WORK) return cudaErrorInvalidValue;
-    // contiguous, cost-balanced partition of the work list into `chunks` chunks
-    int begin[MAX_CHUNKS + 1];
-    double total = 0;
-    for (double c : wcost) total += c;
-    begin[0] = 0;
-    double acc = 0;
-    int k = 1;
-    for (size_t i = 0; i < work.size() && k < chunks; ++i) {
-        acc += wcost[i];
-        if (acc >= total * k / chunks) begin[k++] = (int)i + 1;
+    // contiguous, cost-balanced partition of each half's work list into `chunks` chunks
+    static uint32_t hwork[2][MAX_WORK];
+    int begin[2][MAX_CHUNKS + 1];
+    memset(hwork, 0, sizeof(hwork));
+    for (int hf = 0; hf < 2; ++hf) {
+        if ((int)work[hf].size() > MAX_WORK) return cudaErrorInvalidValue;
+        double total = 0;
+        for (double c : wcost[hf]) total += c;
+        begin[hf][0] = 0;
+        double acc = 0;
+        int k = 1;
+        for (size_t i = 0; i < work[hf].size() && k < chunks; ++i) {
+            acc += wcost[hf][i];
+            if (acc >= total * k / chunks) begin[hf][k++] = (int)i + 1;
+        }
+        while (k <= MAX_CHUNKS) begin[hf][k++] = (int)work[hf].size();
+        memcpy(hwork[hf], work[hf].data(), work[hf].size() * sizeof(uint32_t));
     }
-    while (k <= chunks) begin[k++] = (int)work.size();
-    work.resize(MAX_WORK, 0);
     if ((err = cudaMemcpyToSymbol(c_types, types, sizeof(types))) != cudaSuccess) return err;
-    if ((err = cudaMemcpyToSymbol(c_work, work.data(), sizeof(uint32_t) * MAX_WORK)) != cudaSuccess) return err;
-    if ((err = cudaMemcpyToSymbol(c_chunk_begin, begin, sizeof(int) * (chunks + 1))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_work, hwork, sizeof(hwork))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_chunk_begin, begin, sizeof(begin))) != cudaSuccess) return err;
     // matrices: (coef - 32) as signed bytes in the padded shared-memory layout
     std::vector<uint8_t> mat(MAT_BYTES, 0);
     for (int m = 0; m < 6; ++m)
@@ -581,6 +657,10 @@ cudaError_t kernels_init(int chunks) {
             for (int i = 0; i < 4; ++i) mat[M0_OFF + m * M0_STRIDE + p * 4 + i] = (uint8_t)(int8_t)((int)MIP_MAT_ID0[m][p][i] - 32);
     if ((err = cudaMemcpyToSymbol(g_mat, mat.data(), MAT_BYTES)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(mip_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(mip_cost_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return err;
+    int ctas = 0;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, mip_cost_kernel, NT, SM_TOTAL)) != cudaSuccess) return err;
+    if (getenv("MIPB200_VERBOSE")) fprintf(stderr, "mipb200: cost kernel %d threads, %d B smem, %d CTA(s)/SM, %d chunks per CTU half\n", NT, SM_TOTAL, ctas, chunks);
     g_chunks = chunks;
     return cudaSuccess;
 }
@@ -590,7 +670,7 @@ int kernels_chunks_per_ctu() { return g_chunks; }
 cudaError_t launch_costs(const uint16_t* d_orig, const uint16_t* d_ref, int W, int H, int32_t* d_cost, int32_t* d_sad,
                          int32_t* d_satd, cudaStream_t st) {
     const int nctu = (W >> 7) * ((H + 127) >> 7);
-    mip_cost_kernel<<<nctu * g_chunks, NT, SM_TOTAL, st>>>(d_orig, d_ref, W, H, g_chunks, d_cost, d_sad, d_satd);
+    mip_cost_kernel<<<nctu * 2 * g_chunks, NT, SM_TOTAL, st>>>(d_orig, d_ref, W, H, g_chunks, d_cost, d_sad, d_satd);
     return cudaGetLastError();
 }
 

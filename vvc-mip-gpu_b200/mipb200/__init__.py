@@ -16,7 +16,7 @@ import numpy as np
 from . import tables  # noqa: F401
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "lib", "libmipb200.so")
+LIB_PATH = os.environ.get("MIPB200_LIB") or os.path.join(_PKG, "lib", "libmipb200.so")   # override: A/B builds only
 CLI_PATH = os.path.join(_PKG, "bin", "mipb200_main")
 CSRC = os.path.join(_PKG, "csrc")
 
