@@ -139,9 +139,15 @@ __device__ __forceinline__ int satd4x4(const int (&d)[16]) {
 
 // The original-sample tile holds o + 1, so that the difference against an interpolated sample
 // floor(v / 2^s) costs one LEA.HI:  o - (v >> s) = (o + 1) + (~v >> s)   (two's complement).
-// A difference against a sample p that needs no shift is (o + 1) + ~p.
+// A difference against a sample p that needs no shift is (o + 1) - p - 1.
 __device__ __forceinline__ int diff_shifted(int o1, int nv, int s) { return o1 + (nv >> s); }
-__device__ __forceinline__ int diff_plain(int o1, int p) { return o1 + ~p; }
+__device__ __forceinline__ int diff_plain(int o1, int p) {   // (o + 1) - p - 1 as one IADD3 (the sub is opaque to LLVM,
+    int t;                                                   //  which would otherwise emit LOP3 ~p + IADD)
+    asm("sub.s32 %0, %1, %2;" : "=r"(t) : "r"(o1), "r"(p));
+    return t - 1;
+}
+// clamp to the 10-bit sample range in one VIMNMX.RELU: max(min(v, 1023), 0)   (intra.cl:482)
+__device__ __forceinline__ int clamp10(int v) { return __vimin_s32_relu(v, 1023); }
 
 // One 4x4 block given its 16 differences d = orig - pred (raster): SAD += sum|d| (one VABSDIFF
 // each), SATD += satd4x4(d).
@@ -262,7 +268,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
                 int acc = 32;
                 acc = __dp2a_lo(ipk[0], cw, acc);
                 acc = __dp2a_hi(ipk[1], cw, acc);
-                p[a * 4 + b] = min(max((acc >> 6) + first, 0), 1023);
+                p[a * 4 + b] = clamp10((acc >> 6) + first);
             }
         int d[16];
 #pragma unroll
@@ -290,7 +296,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
                     acc = __dp2a_hi(ipk[1], cw.x, acc);
                     acc = __dp2a_lo(ipk[2], cw.y, acc);
                     acc = __dp2a_hi(ipk[3], cw.y, acc);
-                    v[e] = min(max((acc >> 6) + first, 0), 1023);
+                    v[e] = clamp10((acc >> 6) + first);
                 }
                 c.s_red[((a * R + b) >> 1) * NT] = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
             }
