@@ -1,0 +1,68 @@
+"""The C-ABI library loads and exports every symbol include/mipb200.h declares (no compute calls: no GPU here)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    hdr = open(os.path.join(ROOT, "include", "mipb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(mipb200_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_header_and_python_binding_agree(mip):
+    assert _declared_functions() == sorted(mip.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(mip):
+    lib = ctypes.CDLL(mip.LIB_PATH)
+    for name in _declared_functions():
+        assert hasattr(lib, name), f"{name} is declared in include/mipb200.h but not exported by libmipb200.so"
+
+
+def test_header_compiles_as_c_and_cxx(tmp_path):
+    import subprocess
+    for comp, ext in (("gcc", "c"), ("g++", "cpp")):
+        src = tmp_path / f"t.{ext}"
+        src.write_text('#include "mipb200.h"\nint main(void){ mipb200_config c; c.width = 0; return sizeof(mipb200_result) > 0 ? c.width : 1; }\n')
+        subprocess.run([comp, "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / f"t_{ext}.o")], check=True)
+
+
+def test_struct_layout_matches_ctypes(mip, tmp_path):
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mipb200.h"\nint main(void){ printf("%zu %zu %zu %zu %zu\\n", sizeof(mipb200_config), sizeof(mipb200_result), offsetof(mipb200_result, cost), offsetof(mipb200_result, gpu_ms), offsetof(mipb200_config, emit)); return 0; }\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v) for v in out] == [ctypes.sizeof(mip.Config), ctypes.sizeof(mip.Result), mip.Result.cost.offset, mip.Result.gpu_ms.offset, mip.Config.emit.offset]
+
+
+def test_no_gpu_means_loud_failure_not_fallback(mip):
+    """Without a CUDA device the engine must refuse to exist (there is no CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    import pytest
+    with pytest.raises(mip.MipError) as ei:
+        mip.Engine(256, 128)
+    assert ei.value.code in (-3, -2)
+    assert mip.lib().mipb200_num_ctus(1920, 1080) == 135 and mip.lib().mipb200_num_ctus(3840, 2160) == 510
+
+
+def test_product_never_touches_the_oracle():
+    """Nothing shipped under vvc-mip-gpu_b200/ or include/ may import, link or execute oracle/."""
+    bad = []
+    for base in ("vvc-mip-gpu_b200", "include"):
+        for dp, _, fns in os.walk(os.path.join(ROOT, base)):
+            if os.sep + "lib" in dp or os.sep + "bin" in dp or "__pycache__" in dp:
+                continue
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".cpp", ".h", ".c", "Makefile")):
+                    txt = open(os.path.join(dp, fn), errors="ignore").read()
+                    if re.search(r"oracle[/.]|import oracle|mip_oracle|libmip_oracle", txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad

@@ -1,0 +1,113 @@
+"""The drop-in CLI (csrc/main.cpp -> bin/mipb200_main): flag parsing like boost::program_options (unique prefixes,
+--opt=value / --opt value, short -f/-s/-o/-l), the parameter echo, CSV errors, and -- on the GPU -- the cost log format."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+
+def _cli(mip):
+    if not os.path.exists(mip.CLI_PATH):
+        mip.build()
+    return mip.CLI_PATH
+
+
+def _run(mip, *args, cwd=None):
+    return subprocess.run([_cli(mip), *args], capture_output=True, text=True, cwd=cwd, timeout=600)
+
+
+def test_help_and_missing_required(mip):
+    r = _run(mip, "--help")
+    assert r.returncode == 1 and "--FramesToBeEncoded" in r.stdout and "--KernelIdx" in r.stdout
+    r = _run(mip, "-s", "256x128")
+    assert r.returncode == 1
+    assert "[!] ERROR: FramesToBeEncoded not set." in r.stdout and "[!] ERROR: Input original frames not set." in r.stdout
+    assert "Exiting after finding errors in input parameters" in r.stdout
+
+
+def test_prefix_matching_and_echo(mip, tmp_path):
+    r = _run(mip, "--Frames=1", "--Res", "250x128", "--Orig", "nofile.csv", "--Device=0")
+    assert "-=-= INPUT PARAMETERS =-=-" in r.stdout and "FramesToBeEncoded=1" in r.stdout and "Device Index=0" in r.stdout
+    assert "OutputPreffix log file not set" in r.stdout
+    assert "[!] ERROR: Unsupported resolution 250x128" in r.stdout and r.returncode == 0      # the reference returns 0 here (main.cpp:301-309)
+    r = _run(mip, "--F=1", "-s", "256x128", "-o", "x.csv")      # --F is ambiguous: FramesToBeEncoded / FilterType
+    assert r.returncode == 1 and "ambiguous" in r.stderr
+    r = _run(mip, "--Bogus=1")
+    assert r.returncode == 1 and "unrecognised option" in r.stderr
+
+
+def test_filter_whitelist_and_runtime_alt_switch(mip):
+    r = _run(mip, "-f", "1", "-s", "256x128", "-o", "x.csv", "--UseAlternativeSamples=1", "--Filter=filterFrame_3d", "--KernelIdx=1")
+    assert "FilterType=filterFrame_3d" in r.stdout and "KernelIdx=1" in r.stdout
+    assert "[!] ERROR: Filter type filterFrame_3d not supported" in r.stdout and r.returncode == 0   # exit(0), main.cpp:76
+    r = _run(mip, "-f", "1", "-s", "256x128", "-o", "x.csv", "--UseAlternativeSamples=1")
+    # like the reference, the whitelist check (main.cpp:71-77) fires before the error count is looked at (:79-82)
+    assert "[!] ERROR: Filter not set." in r.stdout and "Filter type  not supported" in r.stdout and r.returncode == 0
+
+
+def test_bad_resolution_string_and_missing_file(mip):
+    r = _run(mip, "-f", "1", "-s", "1920", "-o", "x.csv")
+    assert 'Input resolution "1920" not set properly' in r.stdout
+    r = _run(mip, "-f", "1", "-s", "256x128", "-o", "/nonexistent/x.csv")
+    assert r.returncode == 1 and "error while opening samples files" in r.stderr
+
+
+def test_short_csv_is_an_error(mip, tmp_path):
+    from mipb200 import frames
+    p = tmp_path / "short.csv"
+    frames.write_csv(str(p), [frames.noise_frame(256, 100, 1)])       # 100 lines, 128 needed
+    r = _run(mip, "-f", "1", "-s", "256x128", "-o", str(p))
+    assert r.returncode == 1 and "holds 100 lines, need 128" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_log_matches_oracle(mip, oracle, tmp_path):
+    """2 frames 256x184 through the real CLI/CSV; frame 0's log rows == oracle in the reference's row order and format."""
+    from mipb200 import frames, tables as T
+    fs = [frames.noise_frame(256, 184, 40), frames.natural_frame(256, 184, 41)]
+    csv = tmp_path / "in.csv"
+    frames.write_csv(str(csv), fs)
+    np.testing.assert_array_equal(frames.read_csv(str(csv), 256, 184, 2), np.stack(fs))
+    for extra, ft, kidx in (([], 0, 0), (["--UseAlternativeSamples=1", "--Filter=filterFrame_2d_float_5x5_quarterCtu", "--KernelIdx=2"], 8, 2)):
+        prefix = tmp_path / f"log{ft}"
+        r = _run(mip, "-f", "2", "-s", "256x184", "-o", str(csv), "-l", str(prefix), *extra)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "Current frame 0" in r.stdout and "Current frame 1" in r.stdout
+        assert "Elapsed time (ms) from writing samples to reading distortion (2x)," in r.stdout
+        lines = open(str(prefix) + ".csv").read().splitlines()
+        assert lines[0] == "CTU,cuSizeName,W,H,CU,X,Y,Mode,SAD,SATD,minSadHad"
+        cost, sad, satd = oracle.run_frame(fs[0], ft, kidx, want_sad_satd=True)
+        assert len(lines) - 1 == cost.size
+        want = []
+        for ctu in range(cost.shape[0]):
+            cx, cy = 128 * (ctu % 2), 128 * (ctu // 2)
+            for t in T.TYPES:
+                for cu in range(t.n):
+                    x, y = t.pos(cu)
+                    for m in range(t.modes):
+                        i = T.COST_OFFSETS[t.idx] + cu * t.modes + m
+                        want.append(f"{ctu},{t.name},{t.w},{t.h},{cu},{cx + x},{cy + y},{m},{sad[ctu, i]},{satd[ctu, i]},{cost[ctu, i]}")
+        assert lines[1:] == want
+
+
+@pytest.mark.gpu
+def test_cli_all_frames_and_two_gpu_workers(mip, oracle, tmp_path):
+    """--AllFrames adds a POC column; --NumGpus shards frames (skipped when the box has a single GPU)."""
+    import torch
+    from mipb200 import frames
+    fs = [frames.noise_frame(128, 128, 60 + i) for i in range(3)]
+    csv = tmp_path / "in.csv"
+    frames.write_csv(str(csv), fs)
+    g = 2 if torch.cuda.device_count() >= 2 else 1
+    r = _run(mip, "-f", "3", "-s", "128x128", "-o", str(csv), "-l", str(tmp_path / "all"), "--AllFrames", "--Compat", f"--NumGpus={g}")
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = open(str(tmp_path / "all") + ".csv").read().splitlines()
+    assert lines[0].startswith("POC,CTU,") and len(lines) - 1 == 3 * 97840
+    for poc in range(3):
+        cost = oracle.run_frame(fs[poc])
+        rows = lines[1 + poc * 97840: 1 + (poc + 1) * 97840]
+        assert all(row.startswith(f"{poc},0,") for row in rows[:5])
+        got = np.array([int(row.rsplit(",", 1)[1]) for row in rows], dtype=np.int32)
+        assert np.array_equal(got, cost[0])
+        assert rows[0].split(",")[-3:-1] == ["0", "0"]       # --Compat: SAD/SATD columns print 0 like the reference build
