@@ -40,7 +40,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     uint16_t* h_frame = nullptr;  // pinned
-    uint16_t *d_frame = nullptr, *d_filt = nullptr;
+    uint16_t* d_frame = nullptr;
     int32_t *d_cost = nullptr, *d_sad = nullptr, *d_satd = nullptr, *d_best_cost = nullptr;
     uint8_t* d_best_mode = nullptr;
     int32_t *h_cost = nullptr, *h_sad = nullptr, *h_satd = nullptr, *h_best_cost = nullptr;  // pinned
@@ -64,7 +64,7 @@ struct mipb200_engine {
     int in_flight = 0;
     long long launches = 0;
     cudaStream_t aux_stream = nullptr;
-    uint16_t* d_aux_filt = nullptr;   // scratch filtered frame for mipb200_run_device
+    mipb200::FilterParams fp;         // fused low-pass filter of this configuration
 };
 
 MIPB200_API const char* mipb200_last_error(void) { return g_err; }
@@ -91,7 +91,7 @@ static void free_slot(Slot& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFreeHost(s.h_frame); cudaFreeHost(s.h_cost); cudaFreeHost(s.h_sad); cudaFreeHost(s.h_satd);
     cudaFreeHost(s.h_best_cost); cudaFreeHost(s.h_best_mode);
-    cudaFree(s.d_frame); cudaFree(s.d_filt); cudaFree(s.d_cost); cudaFree(s.d_sad); cudaFree(s.d_satd);
+    cudaFree(s.d_frame); cudaFree(s.d_cost); cudaFree(s.d_sad); cudaFree(s.d_satd);
     cudaFree(s.d_best_cost); cudaFree(s.d_best_mode);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
@@ -106,7 +106,6 @@ MIPB200_API void mipb200_destroy(mipb200_engine* e) {
     cudaSetDevice(e->cfg.device);
     for (auto& s : e->slots) free_slot(s);
     if (e->aux_stream) { cudaStreamSynchronize(e->aux_stream); cudaStreamDestroy(e->aux_stream); }
-    cudaFree(e->d_aux_filt);
     delete e;
 }
 
@@ -138,6 +137,10 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
     e->cu_bytes4 = (size_t)e->n_ctus * MIP_CUS_PER_CTU * sizeof(int32_t);
     e->cu_bytes1 = (size_t)e->n_ctus * MIP_CUS_PER_CTU;
     e->slots.resize(cfg->slots);
+    if (mipb200::make_filter_params(cfg->filter_type, cfg->kernel_idx, &e->fp) != cudaSuccess) {
+        delete e;
+        return fail(MIPB200_EINVAL, "filter parameters of filter_type %d kernel_idx %d failed their exactness check", cfg->filter_type, cfg->kernel_idx);
+    }
     const bool wc = cfg->emit & MIPB200_EMIT_COSTS, ws = cfg->emit & MIPB200_EMIT_SAD_SATD, wd = cfg->emit & MIPB200_EMIT_DECISIONS;
 #define E_TRY(call)                                                                                     \
     do {                                                                                                \
@@ -157,7 +160,6 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
         E_TRY(cudaEventCreate(&s.ev_done));
         E_TRY(cudaHostAlloc((void**)&s.h_frame, e->frame_bytes, cudaHostAllocDefault));
         E_TRY(cudaMalloc((void**)&s.d_frame, e->frame_bytes));
-        if (cfg->filter_type) E_TRY(cudaMalloc((void**)&s.d_filt, e->frame_bytes));
         E_TRY(cudaMalloc((void**)&s.d_cost, e->cost_bytes));   // always needed (decisions read it)
         if (wc) E_TRY(cudaHostAlloc((void**)&s.h_cost, e->cost_bytes, cudaHostAllocDefault));
         if (ws) {
@@ -186,17 +188,11 @@ MIPB200_API uint16_t* mipb200_next_input(mipb200_engine* e) {
     return e->slots[e->head].h_frame;
 }
 
-// filter -> costs -> decisions on `st`; counts launches
-static int enqueue_kernels(mipb200_engine* e, const uint16_t* d_frame, uint16_t* d_filt, int32_t* d_cost, int32_t* d_sad,
+// fused (filter +) costs -> decisions on `st`; counts launches
+static int enqueue_kernels(mipb200_engine* e, const uint16_t* d_frame, int32_t* d_cost, int32_t* d_sad,
                            int32_t* d_satd, uint8_t* d_bm, int32_t* d_bc, cudaStream_t st) {
     const mipb200_config& c = e->cfg;
-    const uint16_t* d_ref = d_frame;
-    if (c.filter_type) {
-        CU_TRY(mipb200::launch_filter(d_frame, d_filt, c.width, c.height, c.filter_type, c.kernel_idx, st));
-        e->launches++;
-        d_ref = d_filt;
-    }
-    CU_TRY(mipb200::launch_costs(d_frame, d_ref, c.width, c.height, d_cost, d_sad, d_satd, st));
+    CU_TRY(mipb200::launch_costs(d_frame, c.width, c.height, e->fp, d_cost, d_sad, d_satd, st));
     e->launches++;
     if (d_bm && d_bc) {
         CU_TRY(mipb200::launch_decide(d_cost, e->n_ctus, d_bm, d_bc, st));
@@ -215,7 +211,7 @@ MIPB200_API int mipb200_submit(mipb200_engine* e, const uint16_t* frame, int64_t
     CU_TRY(cudaEventRecord(s.ev_start, s.stream));
     CU_TRY(cudaMemcpyAsync(s.d_frame, s.h_frame, e->frame_bytes, cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaEventRecord(s.ev_k0, s.stream));
-    int rc = enqueue_kernels(e, s.d_frame, s.d_filt, s.d_cost, s.d_sad, s.d_satd, s.d_best_mode, s.d_best_cost, s.stream);
+    int rc = enqueue_kernels(e, s.d_frame, s.d_cost, s.d_sad, s.d_satd, s.d_best_mode, s.d_best_cost, s.stream);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(s.ev_k1, s.stream));
     if (s.h_cost) CU_TRY(cudaMemcpyAsync(s.h_cost, s.d_cost, e->cost_bytes, cudaMemcpyDeviceToHost, s.stream));
@@ -261,8 +257,7 @@ MIPB200_API int mipb200_run_device(mipb200_engine* e, const uint16_t* d_frame, i
     if (!e || !d_frame || !d_cost) return fail(MIPB200_EINVAL, "engine, d_frame and d_cost are required");
     CU_TRY(cudaSetDevice(e->cfg.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
-    if (e->cfg.filter_type && !e->d_aux_filt) CU_TRY(cudaMalloc((void**)&e->d_aux_filt, e->frame_bytes));
-    return enqueue_kernels(e, d_frame, e->d_aux_filt, d_cost, d_sad, d_satd, d_best_mode, d_best_cost, st);
+    return enqueue_kernels(e, d_frame, d_cost, d_sad, d_satd, d_best_mode, d_best_cost, st);
 }
 
 MIPB200_API int mipb200_filter_device(mipb200_engine* e, const uint16_t* d_frame, uint16_t* d_out, void* stream) {

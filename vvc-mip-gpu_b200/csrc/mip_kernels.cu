@@ -8,6 +8,11 @@
 //          the top and bottom 128x64 halves are independent.  The CTA stages the half's original
 //          samples (as int32 holding o+1, so a 4-pixel row of a 4x4 block is one LDS.128) and the
 //          reference-sample tile with its top/left halo in shared memory; two CTAs share an SM.
+//          The tile arrives as ONE TMA box (cp.async.bulk.tensor.2d, 144x69 uint16 incl. a 3-sample halo,
+//          out-of-frame samples zero-filled by the hardware) signalled on an mbarrier; the CTA then
+//          expands it to the int32 original tile and to the reference tile -- which is where the
+//          "alternative samples" low-pass filter (intra.cl:1639-3823) is applied, so filtered references
+//          never exist in HBM.
 //   lane = one (CU, mode) pair = one output cost.  32 consecutive (CU, mode) pairs of one CU
 //          type form a warp task, so all lanes run the same shape-specialised code, nothing
 //          is reduced across lanes, there is no barrier after staging, and the 32 costs of a
@@ -19,6 +24,7 @@
 // (A.x = arithmetic specification in SURVEY.md Appendix A; file:line = reference repository.)
 #include "mip_kernels.h"
 
+#include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -51,15 +57,22 @@ constexpr int M1_OFF = M2_OFF + 6 * M2_STRIDE, M1_STRIDE = 136;   // 8 x (16 x 8
 constexpr int M0_OFF = M1_OFF + 8 * M1_STRIDE, M0_STRIDE = 68;    // 16 x (16 x 4 B) + 4
 constexpr int MAT_BYTES = M0_OFF + 16 * M0_STRIDE;    // 5296
 
-constexpr int SM_ORIG = 0;
+constexpr int SM_RED = 0;                                      // first: the TMA box lands here (128-byte aligned)
+constexpr int SM_RED_BYTES = RED_WORDS * NT * 4;               // 49152 at NT = 384
+constexpr int SM_ORIG = SM_RED + SM_RED_BYTES;
 constexpr int SM_ORIG_BYTES = TILE_ROWS * OS * 4;              // 33792
 constexpr int SM_REF = SM_ORIG + SM_ORIG_BYTES;
 constexpr int SM_REF_BYTES = REF_ROWS * RS * 2;                // 17680
-constexpr int SM_RED = SM_REF + SM_REF_BYTES;
-constexpr int SM_RED_BYTES = RED_WORDS * NT * 4;               // 49152 at NT = 384
-constexpr int SM_MAT = SM_RED + SM_RED_BYTES;
-constexpr int SM_MISC = SM_MAT + ((MAT_BYTES + 15) / 16) * 16; // s_dc, work counter
-constexpr int SM_TOTAL = SM_MISC + 16;
+constexpr int SM_MAT = SM_REF + SM_REF_BYTES;
+constexpr int SM_MISC = SM_MAT + ((MAT_BYTES + 15) / 16) * 16; // s_dc, work counter, mbarrier
+constexpr int SM_TOTAL = SM_MISC + 32;
+
+// TMA staging box: frame rows tileY-3 .. tileY+65, columns ctuX-8 .. ctuX+135 (halo 3 >= filter radius 2 + the
+// boundary halo 1; 8 columns on the left keep every row 16-byte aligned).  It overlays the s_red scratch.
+constexpr int STG_W = 144, STG_H = 69, STG_X0 = 8, STG_Y0 = 3;
+constexpr int STG_BYTES = STG_W * STG_H * 2;                   // 19872
+static_assert(STG_BYTES <= SM_RED_BYTES, "staging tile must fit into the scratch it overlays");
+static_assert(SM_RED % 128 == 0, "TMA destination must be 128-byte aligned");
 
 constexpr int MAX_CHUNKS = 64;
 constexpr int MAX_WORK = 1700;          // warp tasks per CTU half
@@ -379,18 +392,137 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 }
 
 // ------------------------------------------------------------------------------------------
+// TMA + mbarrier (sm_90+/sm_100a PTX)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// one 2-D box of the frame -> shared memory; completion (bytes) is counted on `bar`
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// Low-pass filter of one sample taken from the staged tile (A.6; same arithmetic as mip_filter_kernel below).
+// (x, y) = frame position; stg points at the staged sample of frame position (x, y); taps outside the frame are
+// excluded by coordinates (the TMA zero fill is never interpreted as a sample).
+// ------------------------------------------------------------------------------------------
+template <int RAD, bool IS2D>
+__device__ __forceinline__ int filter_staged(const uint16_t* stg, int x, int y, int W, int H, int kidx) {
+    int num = 0, den = 0;
+    if constexpr (IS2D) {
+#pragma unroll
+        for (int dy = -RAD; dy <= RAD; ++dy)
+#pragma unroll
+            for (int dx = -RAD; dx <= RAD; ++dx) {
+                const int xx = x + dx, yy = y + dy;
+                if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+                const int k = RAD == 1 ? mip_k3(kidx, dy, dx) : mip_k5(kidx, dy, dx);
+                num += k * (int)stg[dy * STG_W + dx];
+                den += k;
+            }
+    } else {
+        int k[2 * RAD + 1];
+#pragma unroll
+        for (int i = 0; i <= 2 * RAD; ++i) k[i] = RAD == 1 ? mip_k3(kidx, -1, i - 1) : mip_k5(kidx, -2, i - 2);
+#pragma unroll
+        for (int dy = -RAD; dy <= RAD; ++dy) {
+            int hor = 0;
+#pragma unroll
+            for (int dx = -RAD; dx <= RAD; ++dx) {
+                const int xx = x + dx, yy = y + dy;
+                if (xx >= 0 && xx < W && yy >= 0 && yy < H) hor += k[dx + RAD] * (int)stg[dy * STG_W + dx];
+            }
+            num += k[dy + RAD] * hor;
+        }
+        if constexpr (RAD == 1) {
+            const int nEdges = (x == 0) + (x == W - 1) + (y == 0) + (y == H - 1);
+            const int k0 = k[0], k1 = k[1];
+            den = nEdges >= 2 ? (k0 + 2 * k1 + k1 * k1) : (nEdges == 1 ? (2 * k0 + 3 * k1 + k1 * k1) : (4 * k0 + 4 * k1 + k1 * k1));
+        } else {
+            auto ksum = [&](int i0, int j0) {
+                int t = 0;
+                for (int i = i0; i < 5; ++i)
+                    for (int j = j0; j < 5; ++j) t += mip_k5(kidx, i - 2, j - 2);
+                return t;
+            };
+            const bool oTB = (y == 0) || (y == H - 1), iTB = (y == 1) || (y == H - 2);
+            const bool oLR = (x == 0) || (x == W - 1), iLR = (x == 1) || (x == W - 2);
+            const bool oC = oTB && oLR, iC = iTB && iLR;
+            const bool ifc = (oLR && iTB) || (iLR && oTB);
+            const bool oE = !oC && !ifc && (oTB || oLR), iE = !iC && !ifc && (iTB || iLR);
+            den = ksum(0, 0);
+#pragma unroll
+            for (int dy = -2; dy <= 2; ++dy)
+                if (y + dy < 0 || y + dy >= H) den -= k[dy + 2];
+            if (oC) den = ksum(2, 2);
+            if (iC) den = ksum(1, 1);
+            if (oE) den = ksum(0, 2);
+            if (iE) den = ksum(0, 1);
+            if (ifc) den = ksum(1, 2);
+        }
+    }
+    return (num + den / 2) / den;
+}
+
+// Reference tile from the staged tile: a copy (original samples) or the filtered samples.  Only the samples a
+// boundary can touch are produced: the halo row/column, rows and columns = 3 (mod 4) (every CU origin is a
+// multiple of 4), and frame row 0 / frame column 0 for the replicated-sample edge rules.
+template <int RAD, bool IS2D>
+__device__ __forceinline__ void build_ref_tile(uint16_t* s_ref, const uint16_t* stg, int ctuX, int tileY, int W, int H,
+                                               const FilterParams& fp, int tid) {
+    constexpr int N = 2 * RAD + 1;
+    for (int i = tid; i < REF_ROWS * 129; i += NT) {
+        const int r = i / 129, cc = i - r * 129;            // r = 0 <-> frame row tileY - 1; cc = 0 <-> frame column ctuX - 1
+        const int y = tileY - 1 + r, x = ctuX - 1 + cc;
+        const bool needed = r == 0 || cc == 0 || ((r & 3) == 0) || ((cc & 3) == 0) || y == 0 || x == 0;
+        int v = 0;
+        if (needed && x >= 0 && y >= 0 && y < H) {
+            const uint16_t* p = stg + (r + STG_Y0 - 1) * STG_W + (cc + STG_X0 - 1);
+            if (x >= RAD && x < W - RAD && y >= RAD && y < H - RAD) {
+                // whole window inside the frame: fixed weights, fixed denominator, division by multiply-high
+                int num = fp.full_den >> 1;
+#pragma unroll
+                for (int dy = -RAD; dy <= RAD; ++dy)
+#pragma unroll
+                    for (int dx = -RAD; dx <= RAD; ++dx) num += fp.coef[(dy + RAD) * N + dx + RAD] * (int)p[dy * STG_W + dx];
+                v = (int)__umulhi((uint32_t)num, fp.full_magic);
+            } else {
+                v = filter_staged<RAD, IS2D>(p, x, y, W, H, fp.kidx);      // frame border: position classes of A.6
+            }
+        }
+        s_ref[r * RS + cc + 7] = (uint16_t)v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // The fused kernel
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 2)
-mip_cost_kernel(const uint16_t* __restrict__ g_orig, const uint16_t* __restrict__ g_ref, int W, int H,
-                int chunks, int32_t* __restrict__ g_cost, int32_t* __restrict__ g_sad, int32_t* __restrict__ g_satd) {
-    extern __shared__ __align__(16) unsigned char smem[];
+mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams fp, int W, int H, int chunks,
+                int32_t* __restrict__ g_cost, int32_t* __restrict__ g_sad, int32_t* __restrict__ g_satd) {
+    extern __shared__ __align__(128) unsigned char smem[];
     int* s_orig = reinterpret_cast<int*>(smem + SM_ORIG);
     uint16_t* s_ref = reinterpret_cast<uint16_t*>(smem + SM_REF);
     uint32_t* s_red = reinterpret_cast<uint32_t*>(smem + SM_RED);
+    uint16_t* s_stg = reinterpret_cast<uint16_t*>(smem + SM_RED);    // TMA box, dead before the first task starts
     uint8_t* s_mat = smem + SM_MAT;
     uint16_t* s_dc = reinterpret_cast<uint16_t*>(smem + SM_MISC);
     int* s_next = reinterpret_cast<int*>(smem + SM_MISC + 4);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + SM_MISC + 16);
 
     const int tid = threadIdx.x, lane = tid & 31;
     // chunk-major unit order: CTAs that are resident together work on the same chunk (the same CU
@@ -405,28 +537,44 @@ mip_cost_kernel(const uint16_t* __restrict__ g_orig, const uint16_t* __restrict_
     const size_t ctuBase = (size_t)ctu * MIP_COSTS_PER_CTU;
 
     if (rowsValid > 0) {
-        // ---- stage: originals (+1) as int32, 8 pixels per thread per step (coalesced 16-byte loads)
-        for (int i = tid; i < TILE_ROWS * 16; i += NT) {
-            const int y = i >> 4, xc = (i & 15) << 3;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (y < rowsValid) v = __ldg(reinterpret_cast<const uint4*>(g_orig + (size_t)(tileY + y) * W + ctuX + xc));
-            int4* dst = reinterpret_cast<int4*>(s_orig + y * OS + xc);
-            dst[0] = make_int4((v.x & 0xffff) + 1, (v.x >> 16) + 1, (v.y & 0xffff) + 1, (v.y >> 16) + 1);   // o + 1, see diff_shifted()
-            dst[1] = make_int4((v.z & 0xffff) + 1, (v.z >> 16) + 1, (v.w & 0xffff) + 1, (v.w >> 16) + 1);
-        }
-        // ---- stage: reference tile rows -1..63, columns -8..127 (column -1 is the left halo)
-        for (int i = tid; i < REF_ROWS * 17; i += NT) {
-            const int r = i / 17, xc = (i % 17) * 8 - 8;
-            const int y = tileY + r - 1, x = ctuX + xc;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (y >= 0 && y < H && x >= 0) v = __ldg(reinterpret_cast<const uint4*>(g_ref + (size_t)y * W + x));
-            *reinterpret_cast<uint4*>(s_ref + r * RS + xc + 8) = v;
+        // ---- stage: one TMA box (tile + halo) signalled on an mbarrier; the matrices come in meanwhile
+        if (tid == 0) {
+            mbar_init(s_bar, 1);
+            mbar_expect_tx(s_bar, STG_BYTES);
+            tma_load_2d(s_stg, &tmap, ctuX - STG_X0, tileY - STG_Y0, s_bar);
         }
         for (int i = tid; i < MAT_BYTES / 4; i += NT)
             reinterpret_cast<uint32_t*>(s_mat)[i] = reinterpret_cast<const uint32_t*>(g_mat)[i];
+        __syncthreads();                                  // the barrier word is initialised for everyone
+        {
+            int spins = 0;
+            while (!mbar_try_wait(s_bar, 0))
+                if (++spins > (1 << 22)) __trap();        // a lost TMA must not hang the GPU
+        }
+        // ---- originals (+1) as int32 (see diff_shifted()); rows below the frame are TMA zero fill
+        for (int i = tid; i < TILE_ROWS * 16; i += NT) {
+            const int y = i >> 4, xc = (i & 15) << 3;
+            const uint4 v = *reinterpret_cast<const uint4*>(s_stg + (y + STG_Y0) * STG_W + STG_X0 + xc);
+            int4* dst = reinterpret_cast<int4*>(s_orig + y * OS + xc);
+            dst[0] = make_int4((v.x & 0xffff) + 1, (v.x >> 16) + 1, (v.y & 0xffff) + 1, (v.y >> 16) + 1);
+            dst[1] = make_int4((v.z & 0xffff) + 1, (v.z >> 16) + 1, (v.w & 0xffff) + 1, (v.w >> 16) + 1);
+        }
+        // ---- reference tile rows -1..63, columns -1..127: copy, or the fused low-pass filter (ftype = 1..8)
+        switch (fp.type) {
+            case 0:
+                for (int i = tid; i < REF_ROWS * 129; i += NT) {
+                    const int r = i / 129, cc = i - r * 129;
+                    s_ref[r * RS + cc + 7] = s_stg[(r + STG_Y0 - 1) * STG_W + (cc + STG_X0 - 1)];
+                }
+                break;
+            case 1: case 2: build_ref_tile<1, false>(s_ref, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            case 3: case 4: build_ref_tile<1, true>(s_ref, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            case 5: case 6: build_ref_tile<2, false>(s_ref, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            default:        build_ref_tile<2, true>(s_ref, s_stg, ctuX, tileY, W, H, fp, tid); break;
+        }
     }
     if (tid == 0) { *s_dc = 512; *s_next = 0; }
-    __syncthreads();
+    __syncthreads();                                      // tiles complete; the staging box may now be overwritten
 
     Ctx c;
     c.s_orig = s_orig;
@@ -673,10 +821,68 @@ cudaError_t kernels_init(int chunks) {
 
 int kernels_chunks_per_ctu() { return g_chunks; }
 
-cudaError_t launch_costs(const uint16_t* d_orig, const uint16_t* d_ref, int W, int H, int32_t* d_cost, int32_t* d_sad,
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no -lcuda at link time)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static cudaError_t make_frame_map(const uint16_t* d_frame, int W, int H, CUtensorMap* map) {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return e;
+        if (!fn || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+        g_encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)W, (cuuint64_t)H};
+    const cuuint64_t gstride[1] = {(cuuint64_t)W * sizeof(uint16_t)};
+    const cuuint32_t box[2] = {STG_W, STG_H};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t*>(d_frame), gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t make_filter_params(int ft, int kidx, FilterParams* fp) {
+    memset(fp, 0, sizeof(*fp));
+    fp->type = ft;
+    fp->kidx = kidx;
+    fp->full_den = 1;
+    fp->full_magic = 0;
+    if (ft == 0) return cudaSuccess;
+    const bool is5 = ft >= 5, is2d = (ft == 3 || ft == 4 || ft == 7 || ft == 8);
+    const int R = is5 ? 2 : 1, N = 2 * R + 1;
+    int sum2d = 0;
+    for (int dy = -R; dy <= R; ++dy)
+        for (int dx = -R; dx <= R; ++dx) {
+            const int k2 = is5 ? mip_k5(kidx, dy, dx) : mip_k3(kidx, dy, dx);
+            const int k1 = (is5 ? mip_k5(kidx, -2, dy) : mip_k3(kidx, -1, dy)) * (is5 ? mip_k5(kidx, -2, dx) : mip_k3(kidx, -1, dx));
+            fp->coef[(dy + R) * N + dx + R] = is2d ? k2 : k1;     // 1-D types: first row of the table, applied in x and in y
+            sum2d += k2;
+        }
+    if (is2d || is5) fp->full_den = sum2d;                         // 1-D 5x5 takes its interior denominator from the 2-D table
+    else { const int k0 = mip_k3(kidx, -1, -1), k1 = mip_k3(kidx, -1, 0); fp->full_den = 4 * k0 + 4 * k1 + k1 * k1; }
+    fp->full_magic = (uint32_t)((1ull << 32) / fp->full_den + 1);
+    // exactness of the multiply-high division over every numerator that can occur (weights x 1023 + den/2)
+    int wsum = 0;
+    for (int i = 0; i < N * N; ++i) wsum += fp->coef[i];
+    const uint64_t nmax = (uint64_t)wsum * 1023 + fp->full_den / 2;
+    for (uint64_t n = 0; n <= nmax; ++n)
+        if (((n * fp->full_magic) >> 32) != n / fp->full_den) return cudaErrorInvalidValue;
+    return cudaSuccess;
+}
+
+cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, const FilterParams& fp, int32_t* d_cost, int32_t* d_sad,
                          int32_t* d_satd, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(d_frame) & 15) != 0) return cudaErrorMisalignedAddress;   // TMA needs a 16-byte aligned frame
+    CUtensorMap map;
+    cudaError_t e = make_frame_map(d_frame, W, H, &map);
+    if (e != cudaSuccess) return e;
     const int nctu = (W >> 7) * ((H + 127) >> 7);
-    mip_cost_kernel<<<nctu * 2 * g_chunks, NT, SM_TOTAL, st>>>(d_orig, d_ref, W, H, g_chunks, d_cost, d_sad, d_satd);
+    mip_cost_kernel<<<nctu * 2 * g_chunks, NT, SM_TOTAL, st>>>(map, fp, W, H, g_chunks, d_cost, d_sad, d_satd);
     return cudaGetLastError();
 }
 

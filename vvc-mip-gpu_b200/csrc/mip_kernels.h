@@ -9,10 +9,23 @@ namespace mipb200 {
 cudaError_t kernels_init(int chunks_per_ctu);
 int kernels_chunks_per_ctu();
 
-// Fused MIP cost kernel for one frame.  d_orig: samples the distortion is measured against;
-// d_ref: samples the boundaries come from (== d_orig for original-sample mode).
-// cost/sad/satd: [nCTU][97840] int32, sad/satd may be null.
-cudaError_t launch_costs(const uint16_t* d_orig, const uint16_t* d_ref, int W, int H, int32_t* d_cost,
+// Low-pass filter of the fused path, prepared once per engine and passed to the kernel by value (constant-bank
+// operands): the (2R+1)^2 tap weights (k (x) k for the 1-D types), the denominator of a sample whose whole window
+// lies inside the frame, and the multiplier that turns the division by it into a multiply-high.
+struct FilterParams {
+    int type;             // 0 none, 1..8 = availableFilters order
+    int kidx;
+    int coef[25];         // row-major (2R+1) x (2R+1)
+    int full_den;
+    uint32_t full_magic;  // floor(n / full_den) == (n * full_magic) >> 32 for every numerator that can occur (checked)
+};
+cudaError_t make_filter_params(int filter_type, int kernel_idx, FilterParams* fp);
+
+// Fused MIP kernel for one frame: TMA-staged tiles, optional low-pass filter of the reference samples
+// (filter_type 0 = original samples, 1..8 = availableFilters order) applied in shared memory, boundaries,
+// reduced prediction, up-sampling, SAD/SATD.  cost/sad/satd: [nCTU][97840] int32, sad/satd may be null.
+// d_frame must be 16-byte aligned.
+cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, const FilterParams& fp, int32_t* d_cost,
                          int32_t* d_sad, int32_t* d_satd, cudaStream_t st);
 
 // Low-pass filter of a whole frame (alternative samples), filter_type 1..8.
