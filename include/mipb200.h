@@ -96,8 +96,9 @@ int mipb200_num_ctus(int width, int height);
 
 /* Device-resident path: the frame is already in HBM and the results stay there (no host
  * copies).  All pointers are device pointers on the engine's GPU; any output may be NULL.
- * `stream` is a cudaStream_t (NULL = the engine's compute stream).  Asynchronous.
- * This is the fused equivalent of the reference's kernel sequence filterFrame_* ->
+ * `stream` is a cudaStream_t (NULL = the engine's compute stream).  Asynchronous.  d_cost may be NULL when only the
+ * decisions are wanted; d_best_mode and d_best_cost go together; d_frame must be 16-byte aligned (TMA source).
+ * ONE kernel: this is the fused equivalent of the reference's kernel sequence filterFrame_* ->
  * initBoundaries -> MIP_ReducedPred -> upsampleDistortion x3 (main.cpp:723-742, 819-844,
  * 925-946, 1011-1045, 1090-1124, 1167-1200). */
 int mipb200_run_device(mipb200_engine* e, const uint16_t* d_frame, int32_t* d_cost, int32_t* d_sad,

@@ -102,11 +102,23 @@ def test_device_resident_path(mip, oracle):
         eng.run_device(d_in.data_ptr(), d_cost.data_ptr(), d_best_mode=d_bm.data_ptr(), d_best_cost=d_bc.data_ptr(),
                        stream=st.cuda_stream)
         st.synchronize()                      # the work ran on the stream we passed, nowhere else
-        assert eng.kernel_launches() - n0 == 2
+        assert eng.kernel_launches() - n0 == 1          # filter, costs and the per-CU argmin are one fused kernel
         want = oracle.run_frame(f)
         _assert_same(d_cost.cpu().numpy(), want, "device cost")
         bm, bc = oracle.decisions(want)
         _assert_same(d_bm.cpu().numpy(), bm, "device best_mode")
+        _assert_same(d_bc.cpu().numpy(), bc, "device best_cost")
+        # decisions without the cost table, and the stand-alone argmin over an existing table
+        d_bm2, d_bc2 = torch.empty_like(d_bm), torch.empty_like(d_bc)
+        eng.run_device(d_in.data_ptr(), 0, d_best_mode=d_bm2.data_ptr(), d_best_cost=d_bc2.data_ptr(), stream=st.cuda_stream)
+        st.synchronize()
+        _assert_same(d_bm2.cpu().numpy(), bm, "decisions-only best_mode")
+        _assert_same(d_bc2.cpu().numpy(), bc, "decisions-only best_cost")
+        d_bm2.zero_(); d_bc2.zero_(); torch.cuda.synchronize()
+        eng.decide_device(d_cost.data_ptr(), d_bm2.data_ptr(), d_bc2.data_ptr(), stream=st.cuda_stream)
+        st.synchronize()
+        _assert_same(d_bm2.cpu().numpy(), bm, "decide_device best_mode")
+        _assert_same(d_bc2.cpu().numpy(), bc, "decide_device best_cost")
 
 
 def test_errors(mip):

@@ -160,8 +160,10 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
         E_TRY(cudaEventCreate(&s.ev_done));
         E_TRY(cudaHostAlloc((void**)&s.h_frame, e->frame_bytes, cudaHostAllocDefault));
         E_TRY(cudaMalloc((void**)&s.d_frame, e->frame_bytes));
-        E_TRY(cudaMalloc((void**)&s.d_cost, e->cost_bytes));   // always needed (decisions read it)
-        if (wc) E_TRY(cudaHostAlloc((void**)&s.h_cost, e->cost_bytes, cudaHostAllocDefault));
+        if (wc) {   // decisions-only engines never materialise the 97840-entry table
+            E_TRY(cudaMalloc((void**)&s.d_cost, e->cost_bytes));
+            E_TRY(cudaHostAlloc((void**)&s.h_cost, e->cost_bytes, cudaHostAllocDefault));
+        }
         if (ws) {
             E_TRY(cudaMalloc((void**)&s.d_sad, e->cost_bytes));
             E_TRY(cudaMalloc((void**)&s.d_satd, e->cost_bytes));
@@ -188,16 +190,12 @@ MIPB200_API uint16_t* mipb200_next_input(mipb200_engine* e) {
     return e->slots[e->head].h_frame;
 }
 
-// fused (filter +) costs -> decisions on `st`; counts launches
+// one fused kernel per frame: (filter +) boundaries + prediction + costs + per-CU argmin; counts launches
 static int enqueue_kernels(mipb200_engine* e, const uint16_t* d_frame, int32_t* d_cost, int32_t* d_sad,
                            int32_t* d_satd, uint8_t* d_bm, int32_t* d_bc, cudaStream_t st) {
     const mipb200_config& c = e->cfg;
-    CU_TRY(mipb200::launch_costs(d_frame, c.width, c.height, e->fp, d_cost, d_sad, d_satd, st));
+    CU_TRY(mipb200::launch_costs(d_frame, c.width, c.height, e->fp, d_cost, d_sad, d_satd, d_bm, d_bc, st));
     e->launches++;
-    if (d_bm && d_bc) {
-        CU_TRY(mipb200::launch_decide(d_cost, e->n_ctus, d_bm, d_bc, st));
-        e->launches++;
-    }
     return MIPB200_OK;
 }
 
@@ -254,7 +252,9 @@ MIPB200_API int mipb200_collect(mipb200_engine* e, mipb200_result* out) {
 
 MIPB200_API int mipb200_run_device(mipb200_engine* e, const uint16_t* d_frame, int32_t* d_cost, int32_t* d_sad, int32_t* d_satd,
                                    uint8_t* d_best_mode, int32_t* d_best_cost, void* stream) {
-    if (!e || !d_frame || !d_cost) return fail(MIPB200_EINVAL, "engine, d_frame and d_cost are required");
+    if (!e || !d_frame) return fail(MIPB200_EINVAL, "engine and d_frame are required");
+    if (!d_cost && !d_best_mode) return fail(MIPB200_EINVAL, "at least one of d_cost and d_best_mode/d_best_cost is required");
+    if ((d_best_mode == nullptr) != (d_best_cost == nullptr)) return fail(MIPB200_EINVAL, "d_best_mode and d_best_cost go together");
     CU_TRY(cudaSetDevice(e->cfg.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
     return enqueue_kernels(e, d_frame, d_cost, d_sad, d_satd, d_best_mode, d_best_cost, st);

@@ -65,7 +65,8 @@ constexpr int SM_REF = SM_ORIG + SM_ORIG_BYTES;
 constexpr int SM_REF_BYTES = REF_ROWS * RS * 2;                // 17680
 constexpr int SM_MAT = SM_REF + SM_REF_BYTES;
 constexpr int SM_MISC = SM_MAT + ((MAT_BYTES + 15) / 16) * 16; // s_dc, work counter, mbarrier
-constexpr int SM_TOTAL = SM_MISC + 32;
+constexpr int SM_DEC = SM_MISC + 32;                            // u32[DEC_MAX]: min over modes of (cost << 6 | mode)
+constexpr int SM_TOTAL = SM_DEC + 2048 * 4;
 
 // TMA staging box: frame rows tileY-3 .. tileY+65, columns ctuX-8 .. ctuX+135 (halo 3 >= filter radius 2 + the
 // boundary halo 1; 8 columns on the left keep every row 16-byte aligned).  It overlays the s_red scratch.
@@ -83,6 +84,7 @@ struct DevType {
     uint32_t mode_magic;   // task / modes == (task * mode_magic) >> 16 for every task of the type
     uint16_t first_cu[2], n_cu[2];   // CUs of the type that lie in the top / bottom half of the CTU (contiguous in CU order)
     uint8_t parts_log2, pad[3];      // lanes that share one (CU, mode): 4 for 64x64 (a quarter of the strips each), else 1
+    uint16_t cu_ord[2];              // ordinal of the type's first CU among all CUs of the top / bottom half
     uint32_t cost_off, cu_off;
     uint8_t xs[32], ys[32];
 };
@@ -90,6 +92,10 @@ struct DevType {
 __constant__ DevType c_types[MIP_NUM_TYPES];
 __constant__ uint32_t c_work[2][MAX_WORK];     // per half: type | (warp task index inside the type's half) << 8
 __constant__ int c_chunk_begin[2][MAX_CHUNKS + 1];
+// fused decisions: a chunk never splits the modes of a CU, so the CTA owns the argmin of its CUs
+constexpr int DEC_MAX = 2048;                  // CUs per chunk the shared-memory argmin table can hold
+__constant__ uint16_t c_chunk_ord[2][MAX_CHUNKS + 1];   // first CU ordinal of each chunk (per half)
+__constant__ uint16_t c_ord2cu[2][2700];       // CU ordinal inside a half -> CU index inside the CTU (0..5379)
 __device__ uint8_t g_mat[MAT_BYTES];           // (coef - 32) as signed bytes, padded layout above
 
 static int g_chunks = 0;
@@ -513,7 +519,8 @@ __device__ __forceinline__ void build_ref_tile(uint16_t* s_ref, const uint16_t* 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 2)
 mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams fp, int W, int H, int chunks,
-                int32_t* __restrict__ g_cost, int32_t* __restrict__ g_sad, int32_t* __restrict__ g_satd) {
+                int32_t* __restrict__ g_cost, int32_t* __restrict__ g_sad, int32_t* __restrict__ g_satd,
+                uint8_t* __restrict__ g_best_mode, int32_t* __restrict__ g_best_cost) {
     extern __shared__ __align__(128) unsigned char smem[];
     int* s_orig = reinterpret_cast<int*>(smem + SM_ORIG);
     uint16_t* s_ref = reinterpret_cast<uint16_t*>(smem + SM_REF);
@@ -523,6 +530,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     uint16_t* s_dc = reinterpret_cast<uint16_t*>(smem + SM_MISC);
     int* s_next = reinterpret_cast<int*>(smem + SM_MISC + 4);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + SM_MISC + 16);
+    uint32_t* s_dec = reinterpret_cast<uint32_t*>(smem + SM_DEC);
 
     const int tid = threadIdx.x, lane = tid & 31;
     // chunk-major unit order: CTAs that are resident together work on the same chunk (the same CU
@@ -573,6 +581,9 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             default:        build_ref_tile<2, true>(s_ref, s_stg, ctuX, tileY, W, H, fp, tid); break;
         }
     }
+    const int ordBeg = c_chunk_ord[half][chunk], ordCnt = c_chunk_ord[half][chunk + 1] - ordBeg;
+    if (g_best_mode)
+        for (int i = tid; i < ordCnt; i += NT) s_dec[i] = 0xffffffffu;
     if (tid == 0) { *s_dc = 512; *s_next = 0; }
     __syncthreads();                                      // tiles complete; the staging box may now be overwritten
 
@@ -631,9 +642,22 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         }
         if (inRange && part == 0) {
             const size_t o = ctuBase + ty.cost_off + cu * modes + mode;
-            g_cost[o] = active ? min(2 * sad, satd) : -1;   // intra.cl:1166
+            const int cost = min(2 * sad, satd);            // intra.cl:1166
+            if (g_cost) g_cost[o] = active ? cost : -1;
             if (g_sad) g_sad[o] = active ? sad : -1;
             if (g_satd) g_satd[o] = active ? satd : -1;
+            // decision = argmin over the CU's modes, lowest mode wins ties: min of (cost << 6 | mode), cost < 2^24
+            if (g_best_mode && active) atomicMin(&s_dec[ty.cu_ord[half] + cuLocal - ordBeg], ((uint32_t)cost << 6) | (uint32_t)mode);
+        }
+    }
+    if (g_best_mode) {
+        __syncthreads();
+        const size_t cuBase = (size_t)ctu * MIP_CUS_PER_CTU;
+        for (int i = tid; i < ordCnt; i += NT) {
+            const uint32_t v = s_dec[i];
+            const size_t o = cuBase + c_ord2cu[half][ordBeg + i];
+            g_best_mode[o] = v == 0xffffffffu ? (uint8_t)0xFF : (uint8_t)(v & 63u);
+            g_best_cost[o] = v == 0xffffffffu ? -1 : (int32_t)(v >> 6);
         }
     }
 }
@@ -746,6 +770,10 @@ cudaError_t kernels_init(int chunks) {
     memset(types, 0, sizeof(types));
     std::vector<uint32_t> work[2];
     std::vector<double> wcost[2];
+    std::vector<char> cut_ok[2];          // may a chunk boundary follow this warp task? (no CU's modes may be split)
+    std::vector<int> ord_after[2];        // CU ordinal reached after this warp task (valid where cut_ok)
+    static uint16_t ord2cu[2][2700];
+    int ord_total[2] = {0, 0};
     for (int t = 0; t < MIP_NUM_TYPES; ++t) {
         const mip_cu_type_t& s = MIP_TYPES[t];
         DevType& d = types[t];
@@ -773,13 +801,25 @@ cudaError_t kernels_init(int chunks) {
             d.n_cu[hf] = (uint16_t)cnt;
             const double mv = s.size_id == 2 ? 700.0 : (s.size_id == 1 ? 200.0 : 120.0);
             const double c = (mv + 11.0 * s.w * s.h + 2.0 * (s.w + s.h) + 60.0) / (1 << d.parts_log2) + (d.parts_log2 ? mv : 0.0);
-            const int nw = ((cnt * s.modes << d.parts_log2) + 31) / 32;
-            for (int w = 0; w < nw; ++w) { work[hf].push_back((uint32_t)t | ((uint32_t)w << 8)); wcost[hf].push_back(c); }
+            const int per_cu = s.modes << d.parts_log2, ntask = cnt * per_cu;
+            const int nw = (ntask + 31) / 32;
+            d.cu_ord[hf] = (uint16_t)ord_total[hf];
+            for (int w = 0; w < nw; ++w) {
+                work[hf].push_back((uint32_t)t | ((uint32_t)w << 8));
+                wcost[hf].push_back(c);
+                const int done = std::min(ntask, 32 * (w + 1));
+                cut_ok[hf].push_back(done % per_cu == 0);
+                ord_after[hf].push_back(ord_total[hf] + done / per_cu);
+            }
+            for (int k = 0; k < cnt; ++k) ord2cu[hf][ord_total[hf] + k] = (uint16_t)(s.cu_off + d.first_cu[hf] + k);
+            ord_total[hf] += cnt;
+            if (ord_total[hf] > 2700) return cudaErrorInvalidValue;
         }
     }
     // contiguous, cost-balanced partition of each half's work list into `chunks` chunks
     static uint32_t hwork[2][MAX_WORK];
     int begin[2][MAX_CHUNKS + 1];
+    uint16_t chunk_ord[2][MAX_CHUNKS + 1];
     memset(hwork, 0, sizeof(hwork));
     for (int hf = 0; hf < 2; ++hf) {
         if ((int)work[hf].size() > MAX_WORK) return cudaErrorInvalidValue;
@@ -788,16 +828,21 @@ cudaError_t kernels_init(int chunks) {
         begin[hf][0] = 0;
         double acc = 0;
         int k = 1;
+        chunk_ord[hf][0] = 0;
         for (size_t i = 0; i < work[hf].size() && k < chunks; ++i) {
             acc += wcost[hf][i];
-            if (acc >= total * k / chunks) begin[hf][k++] = (int)i + 1;
+            if (acc >= total * k / chunks && cut_ok[hf][i]) { chunk_ord[hf][k] = (uint16_t)ord_after[hf][i]; begin[hf][k++] = (int)i + 1; }
         }
-        while (k <= MAX_CHUNKS) begin[hf][k++] = (int)work[hf].size();
+        while (k <= MAX_CHUNKS) { chunk_ord[hf][k] = (uint16_t)ord_total[hf]; begin[hf][k++] = (int)work[hf].size(); }
+        for (int q = 0; q < chunks; ++q)
+            if (chunk_ord[hf][q + 1] - chunk_ord[hf][q] > DEC_MAX) return cudaErrorInvalidValue;   // use more chunks
         memcpy(hwork[hf], work[hf].data(), work[hf].size() * sizeof(uint32_t));
     }
     if ((err = cudaMemcpyToSymbol(c_types, types, sizeof(types))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_work, hwork, sizeof(hwork))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_chunk_begin, begin, sizeof(begin))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_chunk_ord, chunk_ord, sizeof(chunk_ord))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_ord2cu, ord2cu, sizeof(ord2cu))) != cudaSuccess) return err;
     // matrices: (coef - 32) as signed bytes in the padded shared-memory layout
     std::vector<uint8_t> mat(MAT_BYTES, 0);
     for (int m = 0; m < 6; ++m)
@@ -876,13 +921,14 @@ cudaError_t make_filter_params(int ft, int kidx, FilterParams* fp) {
 }
 
 cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, const FilterParams& fp, int32_t* d_cost, int32_t* d_sad,
-                         int32_t* d_satd, cudaStream_t st) {
+                         int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, cudaStream_t st) {
+    if ((d_best_mode == nullptr) != (d_best_cost == nullptr)) return cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(d_frame) & 15) != 0) return cudaErrorMisalignedAddress;   // TMA needs a 16-byte aligned frame
     CUtensorMap map;
     cudaError_t e = make_frame_map(d_frame, W, H, &map);
     if (e != cudaSuccess) return e;
     const int nctu = (W >> 7) * ((H + 127) >> 7);
-    mip_cost_kernel<<<nctu * 2 * g_chunks, NT, SM_TOTAL, st>>>(map, fp, W, H, g_chunks, d_cost, d_sad, d_satd);
+    mip_cost_kernel<<<nctu * 2 * g_chunks, NT, SM_TOTAL, st>>>(map, fp, W, H, g_chunks, d_cost, d_sad, d_satd, d_best_mode, d_best_cost);
     return cudaGetLastError();
 }
 

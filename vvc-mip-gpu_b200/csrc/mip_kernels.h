@@ -25,8 +25,10 @@ cudaError_t make_filter_params(int filter_type, int kernel_idx, FilterParams* fp
 // (filter_type 0 = original samples, 1..8 = availableFilters order) applied in shared memory, boundaries,
 // reduced prediction, up-sampling, SAD/SATD.  cost/sad/satd: [nCTU][97840] int32, sad/satd may be null.
 // d_frame must be 16-byte aligned.
+// d_best_mode/d_best_cost (both or neither): per-CU argmin over the modes, produced by the same kernel.
+// d_cost may be null when only the decisions are wanted.
 cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, const FilterParams& fp, int32_t* d_cost,
-                         int32_t* d_sad, int32_t* d_satd, cudaStream_t st);
+                         int32_t* d_sad, int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, cudaStream_t st);
 
 // Low-pass filter of a whole frame (alternative samples), filter_type 1..8.
 cudaError_t launch_filter(const uint16_t* d_in, uint16_t* d_out, int W, int H, int filter_type, int kernel_idx,

@@ -195,7 +195,7 @@ class Engine:
     # ---- device-resident path (raw device pointers, e.g. torch tensors' data_ptr())
     def run_device(self, d_frame: int, d_cost: int, d_sad: int = 0, d_satd: int = 0, d_best_mode: int = 0,
                    d_best_cost: int = 0, stream: int = 0) -> None:
-        _check(lib().mipb200_run_device(self._h, d_frame, d_cost, d_sad or None, d_satd or None,
+        _check(lib().mipb200_run_device(self._h, d_frame, d_cost or None, d_sad or None, d_satd or None,
                                         d_best_mode or None, d_best_cost or None, stream or None))
 
     def filter_device(self, d_frame: int, d_out: int, stream: int = 0) -> None:
