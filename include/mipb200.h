@@ -83,8 +83,10 @@ uint16_t* mipb200_next_input(mipb200_engine* e);
 
 /* Enqueue one frame: async H2D from the pinned slot, filter (if any), MIP costs, decisions,
  * async D2H.  `frame` = height*width uint16 row-major, samples 0..1023 (main.cpp:364-384);
- * it is copied into the pinned slot unless it already is mipb200_next_input().  Returns
- * immediately.  Replaces one iteration of the frame loop, main.cpp:678-1241. */
+ * Pageable memory is first copied into the slot's pinned buffer; a frame that already lives in
+ * page-locked memory (mipb200_next_input(), cudaHostAlloc/cudaHostRegister) is DMA'd in place and
+ * must then stay untouched until the frame has been collected.  Returns immediately.
+ * Replaces one iteration of the frame loop, main.cpp:678-1241. */
 int mipb200_submit(mipb200_engine* e, const uint16_t* frame, int64_t poc);
 
 /* Wait for the oldest frame in flight and expose its results (FIFO).

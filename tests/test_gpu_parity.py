@@ -131,3 +131,22 @@ def test_errors(mip):
     with mip.Engine(256, 128, slots=1) as eng:
         with pytest.raises(mip.MipError):
             eng.collect()
+
+
+def test_submit_from_callers_pinned_memory(mip, oracle):
+    """A frame that already lives in page-locked memory is DMA'd in place (no staging copy); same result."""
+    import torch
+    from mipb200 import frames
+    fs = [frames.noise_frame(256, 128, 70 + i) for i in range(4)]
+    pin = torch.empty((4, 128, 256), dtype=torch.int16, pin_memory=True)
+    pin.numpy()[...] = np.stack(fs).view(np.int16)
+    with mip.Engine(256, 128, slots=2, emit=mip.EMIT_COSTS) as eng:
+        got = []
+        for i in range(4):
+            eng.submit(pin[i].numpy().view(np.uint16), poc=i)
+            if eng.in_flight() == 2:
+                got.append(eng.collect().cost.copy())
+        while eng.in_flight():
+            got.append(eng.collect().cost.copy())
+    for g, f in zip(got, fs):
+        _assert_same(g, oracle.run_frame(f), "pinned-source cost")

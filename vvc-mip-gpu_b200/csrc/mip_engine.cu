@@ -204,10 +204,17 @@ MIPB200_API int mipb200_submit(mipb200_engine* e, const uint16_t* frame, int64_t
     if (e->in_flight >= (int)e->slots.size()) return fail(MIPB200_EBUSY, "all %d slots in flight; collect first", (int)e->slots.size());
     CU_TRY(cudaSetDevice(e->cfg.device));
     Slot& s = e->slots[e->head];
-    if (frame != s.h_frame) memcpy(s.h_frame, frame, e->frame_bytes);
+    // Source of the H2D DMA: the slot's own pinned buffer, the caller's buffer if that is page-locked already
+    // (cudaHostAlloc / cudaHostRegister / torch pin_memory: no staging copy), else a staging copy of pageable memory.
+    const uint16_t* src = s.h_frame;
+    if (frame != s.h_frame) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, frame) == cudaSuccess && attr.type == cudaMemoryTypeHost) src = frame;
+        else { cudaGetLastError(); memcpy(s.h_frame, frame, e->frame_bytes); }
+    }
     s.poc = poc;
     CU_TRY(cudaEventRecord(s.ev_start, s.stream));
-    CU_TRY(cudaMemcpyAsync(s.d_frame, s.h_frame, e->frame_bytes, cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(cudaMemcpyAsync(s.d_frame, src, e->frame_bytes, cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaEventRecord(s.ev_k0, s.stream));
     int rc = enqueue_kernels(e, s.d_frame, s.d_cost, s.d_sad, s.d_satd, s.d_best_mode, s.d_best_cost, s.stream);
     if (rc) return rc;
