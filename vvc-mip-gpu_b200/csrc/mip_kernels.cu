@@ -47,9 +47,12 @@ namespace mipb200 {
 constexpr int NT = MIP_NT;              // threads per CTA
 constexpr int NWARPS = NT / 32;
 constexpr int OS = 132;                 // s_orig row stride in int32 words (128 + 4: rows shift 4 banks)
-constexpr int RS = 136;                 // s_ref row stride in uint16 (8 halo/alignment + 128)
+// Reference samples are only ever read on the row above / the column left of a CU, and every CU origin is a multiple
+// of 4: the reference tile keeps 18 row slots (halo row -1, rows 3,7,..,63, frame row 0) and 34 column slots (halo
+// column -1, columns 3,7,..,127, frame column 0), the columns stored transposed so that a left boundary is contiguous.
+constexpr int RT_STRIDE = 136, RT_SLOTS = 18, RT_ROW0 = 17;   // row slot: [x + 8], x = -8..127
+constexpr int RL_STRIDE = 72, RL_SLOTS = 34, RL_COL0 = 33;    // column slot: [y + 8], y = -8..63
 constexpr int TILE_ROWS = 64;            // a CTA works on the top or bottom half of a CTU
-constexpr int REF_ROWS = TILE_ROWS + 1;  // rows -1..63
 constexpr int RED_WORDS = 32;           // packed reduced-prediction words per thread (64 samples)
 
 constexpr int M2_OFF = 0, M2_STRIDE = 520;            // 6 x (64 x 8 B), +8 B pad against bank aliasing
@@ -62,7 +65,7 @@ constexpr int SM_RED_BYTES = RED_WORDS * NT * 4;               // 49152 at NT = 
 constexpr int SM_ORIG = SM_RED + SM_RED_BYTES;
 constexpr int SM_ORIG_BYTES = TILE_ROWS * OS * 4;              // 33792
 constexpr int SM_REF = SM_ORIG + SM_ORIG_BYTES;
-constexpr int SM_REF_BYTES = REF_ROWS * RS * 2;                // 17680
+constexpr int SM_REF_BYTES = (RT_SLOTS * RT_STRIDE + RL_SLOTS * RL_STRIDE) * 2;   // 9792
 constexpr int SM_MAT = SM_REF + SM_REF_BYTES;
 constexpr int SM_MISC = SM_MAT + ((MAT_BYTES + 15) / 16) * 16; // s_dc, work counter, mbarrier
 constexpr int SM_DEC = SM_MISC + 32;                            // u32[DEC_MAX]: min over modes of (cost << 6 | mode)
@@ -121,7 +124,8 @@ static int shape_of(int w, int h) {
 // ------------------------------------------------------------------------------------------
 struct Ctx {
     const int* s_orig;        // [128][OS], holds orig + 1
-    const uint16_t* s_ref0;   // element (0,0) of the reference tile; (y,x) at y*RS + x, y,x >= -1
+    const uint16_t* s_refT;   // row slots:    sample (slot, x) at slot * RT_STRIDE + 8 + x
+    const uint16_t* s_refL;   // column slots: sample (slot, y) at slot * RL_STRIDE + 8 + y
     const uint16_t* s_dc;     // one cell holding 512
     uint32_t* s_red;          // this thread's column of the [RED_WORDS][NT] scratch
     const uint8_t* s_mat;
@@ -233,12 +237,12 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
     const int absX = c.ctuX + cuX, absY = c.tileY + cuY;
     const uint16_t *T, *L;
     int stT, stL;
-    if (absY > 0) { T = c.s_ref0 + (cuY - 1) * RS + cuX; stT = 1; }
+    if (absY > 0) { T = c.s_refT + (cuY >> 2) * RT_STRIDE + 8 + cuX; stT = 1; }          // row Y-1 = slot cuY/4
     else if (absX == 0) { T = c.s_dc; stT = 0; }
-    else { T = c.s_ref0 + cuX - 1; stT = 0; }                 // F[0][X-1] replicated
-    if (absX > 0) { L = c.s_ref0 + cuY * RS + cuX - 1; stL = RS; }
+    else { T = c.s_refT + RT_ROW0 * RT_STRIDE + 8 + cuX - 1; stT = 0; }                   // F[0][X-1] replicated
+    if (absX > 0) { L = c.s_refL + (cuX >> 2) * RL_STRIDE + 8 + cuY; stL = 1; }          // column X-1 = slot cuX/4
     else if (absY == 0) { L = c.s_dc; stL = 0; }
-    else { L = c.s_ref0 + (cuY - 1) * RS; stL = 0; }          // F[Y-1][0] replicated
+    else { L = c.s_refL + RL_COL0 * RL_STRIDE + 8 + cuY - 1; stL = 0; }                   // F[Y-1][0] replicated
 
     // ---- A.2 reduced boundaries (intra.cl:127-141, 260-279)
     constexpr int DT = W / B, DL = H / B;
@@ -484,21 +488,36 @@ __device__ __forceinline__ int filter_staged(const uint16_t* stg, int x, int y, 
     return (num + den / 2) / den;
 }
 
-// Reference tile from the staged tile: a copy (original samples) or the filtered samples.  Only the samples a
-// boundary can touch are produced: the halo row/column, rows and columns = 3 (mod 4) (every CU origin is a
-// multiple of 4), and frame row 0 / frame column 0 for the replicated-sample edge rules.
-template <int RAD, bool IS2D>
-__device__ __forceinline__ void build_ref_tile(uint16_t* s_ref, const uint16_t* stg, int ctuX, int tileY, int W, int H,
-                                               const FilterParams& fp, int tid) {
+// Reference tile from the staged tile: a copy (FT == 0, original samples) or the low-pass filtered samples.
+// Item i < RT_SLOTS*129 is sample cc (frame column ctuX-1+cc) of row slot i/129; the rest are the column slots.
+// Frame position -> (slot): rows tileY-1, tileY+3, .., tileY+63 and frame row 0 (slot RT_ROW0, only when tileY == 0);
+// columns ctuX-1, ctuX+3, .., ctuX+127 and frame column 0 (slot RL_COL0, only when ctuX == 0).
+template <int RAD, bool IS2D, bool FILTER>
+__device__ __forceinline__ void build_ref_tile(uint16_t* s_refT, uint16_t* s_refL, const uint16_t* stg, int ctuX, int tileY,
+                                               int W, int H, const FilterParams& fp, int tid) {
     constexpr int N = 2 * RAD + 1;
-    for (int i = tid; i < REF_ROWS * 129; i += NT) {
-        const int r = i / 129, cc = i - r * 129;            // r = 0 <-> frame row tileY - 1; cc = 0 <-> frame column ctuX - 1
-        const int y = tileY - 1 + r, x = ctuX - 1 + cc;
-        const bool needed = r == 0 || cc == 0 || ((r & 3) == 0) || ((cc & 3) == 0) || y == 0 || x == 0;
+    constexpr int NROW = RT_SLOTS * 129, NCOL = RL_SLOTS * 65;
+    for (int i = tid; i < NROW + NCOL; i += NT) {
+        int ty, tx;             // tile-relative position of the sample: ty in -1..63, tx in -1..127
+        uint16_t* dst;
+        if (i < NROW) {
+            const int slot = i / 129, cc = i - slot * 129;
+            ty = slot == RT_ROW0 ? 0 : 4 * slot - 1;
+            tx = cc - 1;
+            dst = s_refT + slot * RT_STRIDE + 8 + tx;
+        } else {
+            const int k = i - NROW, slot = k / 65, rr = k - slot * 65;
+            tx = slot == RL_COL0 ? 0 : 4 * slot - 1;
+            ty = rr - 1;
+            dst = s_refL + slot * RL_STRIDE + 8 + ty;
+        }
+        const int y = tileY + ty, x = ctuX + tx;
         int v = 0;
-        if (needed && x >= 0 && y >= 0 && y < H) {
-            const uint16_t* p = stg + (r + STG_Y0 - 1) * STG_W + (cc + STG_X0 - 1);
-            if (x >= RAD && x < W - RAD && y >= RAD && y < H - RAD) {
+        if (x >= 0 && y >= 0 && y < H) {
+            const uint16_t* p = stg + (ty + STG_Y0) * STG_W + (tx + STG_X0);
+            if constexpr (!FILTER) {
+                v = *p;
+            } else if (x >= RAD && x < W - RAD && y >= RAD && y < H - RAD) {
                 // whole window inside the frame: fixed weights, fixed denominator, division by multiply-high
                 int num = fp.full_den >> 1;
 #pragma unroll
@@ -510,7 +529,7 @@ __device__ __forceinline__ void build_ref_tile(uint16_t* s_ref, const uint16_t* 
                 v = filter_staged<RAD, IS2D>(p, x, y, W, H, fp.kidx);      // frame border: position classes of A.6
             }
         }
-        s_ref[r * RS + cc + 7] = (uint16_t)v;
+        *dst = (uint16_t)v;
     }
 }
 
@@ -523,7 +542,8 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 uint8_t* __restrict__ g_best_mode, int32_t* __restrict__ g_best_cost) {
     extern __shared__ __align__(128) unsigned char smem[];
     int* s_orig = reinterpret_cast<int*>(smem + SM_ORIG);
-    uint16_t* s_ref = reinterpret_cast<uint16_t*>(smem + SM_REF);
+    uint16_t* s_refT = reinterpret_cast<uint16_t*>(smem + SM_REF);
+    uint16_t* s_refL = s_refT + RT_SLOTS * RT_STRIDE;
     uint32_t* s_red = reinterpret_cast<uint32_t*>(smem + SM_RED);
     uint16_t* s_stg = reinterpret_cast<uint16_t*>(smem + SM_RED);    // TMA box, dead before the first task starts
     uint8_t* s_mat = smem + SM_MAT;
@@ -567,18 +587,13 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             dst[0] = make_int4((v.x & 0xffff) + 1, (v.x >> 16) + 1, (v.y & 0xffff) + 1, (v.y >> 16) + 1);
             dst[1] = make_int4((v.z & 0xffff) + 1, (v.z >> 16) + 1, (v.w & 0xffff) + 1, (v.w >> 16) + 1);
         }
-        // ---- reference tile rows -1..63, columns -1..127: copy, or the fused low-pass filter (ftype = 1..8)
+        // ---- reference row/column slots: copy, or the fused low-pass filter (fp.type = 1..8)
         switch (fp.type) {
-            case 0:
-                for (int i = tid; i < REF_ROWS * 129; i += NT) {
-                    const int r = i / 129, cc = i - r * 129;
-                    s_ref[r * RS + cc + 7] = s_stg[(r + STG_Y0 - 1) * STG_W + (cc + STG_X0 - 1)];
-                }
-                break;
-            case 1: case 2: build_ref_tile<1, false>(s_ref, s_stg, ctuX, tileY, W, H, fp, tid); break;
-            case 3: case 4: build_ref_tile<1, true>(s_ref, s_stg, ctuX, tileY, W, H, fp, tid); break;
-            case 5: case 6: build_ref_tile<2, false>(s_ref, s_stg, ctuX, tileY, W, H, fp, tid); break;
-            default:        build_ref_tile<2, true>(s_ref, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            case 0:         build_ref_tile<1, true, false>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            case 1: case 2: build_ref_tile<1, false, true>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            case 3: case 4: build_ref_tile<1, true, true>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            case 5: case 6: build_ref_tile<2, false, true>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            default:        build_ref_tile<2, true, true>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
         }
     }
     const int ordBeg = c_chunk_ord[half][chunk], ordCnt = c_chunk_ord[half][chunk + 1] - ordBeg;
@@ -589,7 +604,8 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 
     Ctx c;
     c.s_orig = s_orig;
-    c.s_ref0 = s_ref + RS + 8;
+    c.s_refT = s_refT;
+    c.s_refL = s_refL;
     c.s_dc = s_dc;
     c.s_red = s_red + tid;
     c.s_mat = s_mat;
