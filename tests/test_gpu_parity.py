@@ -150,3 +150,18 @@ def test_submit_from_callers_pinned_memory(mip, oracle):
             got.append(eng.collect().cost.copy())
     for g, f in zip(got, fs):
         _assert_same(g, oracle.run_frame(f), "pinned-source cost")
+
+
+@pytest.mark.parametrize("shape", [(4, 128), (8, 128), (12, 256), (60, 128), (64, 256), (68, 128), (132, 384)])
+@pytest.mark.parametrize("ft,kidx", [(0, 0), (7, 1), (2, 3), (5, 0)])
+def test_ragged_heights(mip, oracle, shape, ft, kidx):
+    """Heights that leave one, a few or no valid rows in a tile half (skipped halves, 4-row frames, 1 row past a half)."""
+    from mipb200 import frames
+    h, w = shape
+    f = frames.noise_frame(w, h, 90 + h)
+    got = _run(mip, f, ft, kidx, emit=mip.EMIT_COSTS | mip.EMIT_DECISIONS)
+    want = oracle.run_frame(f, ft, kidx)
+    _assert_same(got["cost"], want, f"cost {w}x{h} ft={ft}")
+    bm, bc = oracle.decisions(want)
+    _assert_same(got["best_mode"], bm, "best_mode")
+    _assert_same(got["best_cost"], bc, "best_cost")
