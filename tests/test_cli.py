@@ -111,3 +111,39 @@ def test_cli_all_frames_and_two_gpu_workers(mip, oracle, tmp_path):
         got = np.array([int(row.rsplit(",", 1)[1]) for row in rows], dtype=np.int32)
         assert np.array_equal(got, cost[0])
         assert rows[0].split(",")[-3:-1] == ["0", "0"]       # --Compat: SAD/SATD columns print 0 like the reference build
+
+
+def test_unknown_input_format(mip, tmp_path):
+    p = tmp_path / "x.bin"
+    p.write_bytes(b"\0" * 16)
+    r = _run(mip, "-f", "1", "-s", "128x4", "-o", str(p), "--InputFormat=png")
+    assert r.returncode == 1 and "InputFormat png not supported" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_binary_input_and_decisions_log(mip, oracle, tmp_path):
+    """Raw u16 and 8-bit yuv420p inputs, --NoLog --DecisionsLog: per-CU best mode / cost of every frame == oracle."""
+    from mipb200 import frames, tables as T
+    fs = [frames.natural_frame(256, 128, 80 + i) for i in range(3)]
+    raw = tmp_path / "in.u16"
+    np.stack(fs).astype("<u2").tofile(str(raw))
+    f8 = [(f >> 2).astype(np.uint8) for f in fs]                       # 8-bit content, values used as they are
+    yuv = tmp_path / "in.yuv"
+    with open(yuv, "wb") as fh:
+        for f in f8:
+            fh.write(f.tobytes())
+            fh.write(bytes(256 * 128 // 2))                              # U and V planes
+    for path, fmt, src in ((raw, "u16", fs), (yuv, "yuv420p", [f.astype(np.uint16) for f in f8])):
+        dec = tmp_path / f"dec_{fmt}.csv"
+        r = _run(mip, "-f", "3", "-s", "256x128", "-o", str(path), f"--InputFormat={fmt}", "--NoLog", f"--DecisionsLog={dec}",
+                 "--UseAlternativeSamples=1", "--FilterType=filterFrame_1d_int_5x5", "--KernelIdx=2")
+        assert r.returncode == 0, r.stdout + r.stderr
+        lines = open(dec).read().splitlines()
+        assert lines[0] == "POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost" and len(lines) - 1 == 3 * 2 * 5380
+        for poc in range(3):
+            bm, bc = oracle.decisions(oracle.run_frame(src[poc], 5, 2))
+            rows = lines[1 + poc * 10760: 1 + (poc + 1) * 10760]
+            got_m = np.array([int(x.split(",")[-2]) for x in rows]).reshape(2, 5380)
+            got_c = np.array([int(x.split(",")[-1]) for x in rows]).reshape(2, 5380)
+            assert np.array_equal(got_m, bm) and np.array_equal(got_c, bc)
+            assert rows[0].startswith(f"{poc},0,ALL_AL_64x64,64,64,0,0,0,") and rows[5380].startswith(f"{poc},1,ALL_AL_64x64,64,64,0,128,0,")

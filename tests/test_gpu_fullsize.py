@@ -80,3 +80,18 @@ def test_shard_count_does_not_change_results(mip):
     merged = shard.merge_in_poc_order(per_rank, 6)
     for poc in range(6):
         _eq(merged[poc], one[poc], f"poc {poc}")
+
+
+def test_filter_fusion_exactness_sweep_1080p(mip, oracle):
+    """BASELINE config 3: every filterFrame_* type x every KernelIdx (32 combinations) over the 16 synthetic 1080p frames
+    (4 content classes x 4 seeds: noise, natural, extremes, impulses).  Each frame is evaluated under two combinations,
+    every combination once; full 1080p cost tables compared with the oracle bit for bit."""
+    from mipb200 import frames, tables as T
+    fs = frames.sweep_frames(1920, 1080)
+    combos = [(ft, k) for ft in range(1, 9) for k in range(T.num_kernel_idx(ft))]
+    assert len(fs) == 16 and len(combos) == 32
+    for i, (ft, k) in enumerate(combos):
+        f = fs[i % 16]
+        with mip.Engine(1920, 1080, filter_type=ft, kernel_idx=k, slots=1, emit=mip.EMIT_COSTS) as eng:
+            got = eng.run(f).cost.copy()
+        _eq(got, oracle.run_frame(f, ft, k), f"frame {i % 16} filter_type={ft} kernel_idx={k}")

@@ -13,7 +13,9 @@
 // Extensions (all off by default): --NumGpus G (frames sharded poc % G over G GPUs, one host
 // thread each, no collective), --AllFrames (log every frame with a leading POC column),
 // --Compat (print 0 in the SAD/SATD columns like the reference's MAX_PERFORMANCE_DIST build),
-// --NoLog (skip the text log).
+// --NoLog (skip the text log), --InputFormat csv|u16|yuv420p|yuv420p10le (binary luma input instead of
+// the 2 M stoi() calls per 1080p frame), --DecisionsLog FILE (per-CU best mode + cost of EVERY frame,
+// keyed by POC,X,Y,W,H: the table an encoder-side consumer ingests).
 //
 // The device work goes through the C ABI of include/mipb200.h only.
 #include <errno.h>
@@ -51,12 +53,14 @@ struct Options {
     int kernelIdx = 0;     bool kernelSet = false;
     int useAlt = USE_ALTERNATIVE_SAMPLES;
     int numGpus = 1;
+    std::string inputFormat = "csv", decisionsLog;
     bool allFrames = false, compat = false, noLog = false, help = false;
 };
 
 const char* kLongOpts[] = {"help", "DeviceIndex", "FramesToBeEncoded", "Resolution", "OriginalFrames", "OutputPreffix",
-                           "FilterType", "KernelIdx", "UseAlternativeSamples", "NumGpus", "AllFrames", "Compat", "NoLog"};
-const bool kTakesValue[] = {false, true, true, true, true, true, true, true, true, true, false, false, false};
+                           "FilterType", "KernelIdx", "UseAlternativeSamples", "NumGpus", "AllFrames", "Compat", "NoLog",
+                           "InputFormat", "DecisionsLog"};
+const bool kTakesValue[] = {false, true, true, true, true, true, true, true, true, true, false, false, false, true, true};
 constexpr int kNumOpts = sizeof(kLongOpts) / sizeof(kLongOpts[0]);
 
 void print_help() {
@@ -71,7 +75,9 @@ void print_help() {
            "  --KernelIdx arg (=0)           Index of the filtering kernel used to define the coefficients\n"
            "  --UseAlternativeSamples arg    0|1, run-time form of the USE_ALTERNATIVE_SAMPLES macro\n"
            "  --NumGpus arg (=1)             shard frames over this many GPUs\n"
-           "  --AllFrames --Compat --NoLog   log every frame / zero SAD,SATD columns / no text log\n");
+           "  --AllFrames --Compat --NoLog   log every frame / zero SAD,SATD columns / no text log\n"
+           "  --InputFormat arg (=csv)       csv | u16 (raw little-endian luma) | yuv420p | yuv420p10le\n"
+           "  --DecisionsLog arg             write POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost for every frame\n");
 }
 
 // resolves a (possibly abbreviated) long option; -1 unknown, -2 ambiguous
@@ -142,6 +148,8 @@ bool parse_args(int argc, char** argv, Options& o) {
             case 10: o.allFrames = true; break;
             case 11: o.compat = true; break;
             case 12: o.noLog = true; break;
+            case 13: o.inputFormat = val; break;
+            case 14: o.decisionsLog = val; break;
         }
         if (!ok) { fprintf(stderr, "the argument ('%s') for option '--%s' is invalid\n", val.c_str(), kLongOpts[opt]); return false; }
     }
@@ -217,6 +225,32 @@ bool read_frames_csv(const std::string& path, int W, int H, int N, std::vector<u
     return true;
 }
 
+// Binary luma input: u16 = W*H little-endian uint16 per frame; yuv420p = 8-bit planar 4:2:0 (chroma skipped);
+// yuv420p10le = 16-bit planar 4:2:0.  Sample values are taken as they are (the pipeline is 10-bit, intra.cl:61).
+bool read_frames_binary(const std::string& path, const std::string& fmt, int W, int H, int N, std::vector<uint16_t>& out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { perror("error while opening samples files"); return false; }
+    const size_t px = (size_t)W * H;
+    out.resize(px * N);
+    const bool eight = fmt == "yuv420p";
+    const size_t chroma = fmt == "u16" ? 0 : px / 2 * (eight ? 1 : 2);
+    std::vector<uint8_t> tmp(eight ? px : 0);
+    for (int n = 0; n < N; ++n) {
+        uint16_t* dst = out.data() + px * n;
+        size_t got;
+        if (eight) {
+            got = fread(tmp.data(), 1, px, f);
+            for (size_t i = 0; i < px; ++i) dst[i] = tmp[i];
+        } else {
+            got = fread(dst, 2, px, f);
+        }
+        if (got != px) { fprintf(stderr, "[!] ERROR: %s holds fewer than %d frames of %dx%d (%s)\n", path.c_str(), N, W, H, fmt.c_str()); fclose(f); return false; }
+        if (chroma && fseek(f, (long)chroma, SEEK_CUR) != 0) { fclose(f); return false; }
+    }
+    fclose(f);
+    return true;
+}
+
 // ---- cost log (main_aux_functions.h:735-798)
 struct LogBuf {
     FILE* f;
@@ -264,11 +298,34 @@ void write_frame_log(LogBuf& lb, long poc, bool withPoc, const int32_t* cost, co
     }
 }
 
+// per-CU decisions of one frame: POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost (skipped CUs: 255,-1)
+void write_decisions(LogBuf& lb, long poc, const uint8_t* bm, const int32_t* bc, int nCtus, int W) {
+    const int ctuCols = (W + 127) / 128;
+    for (int ctu = 0; ctu < nCtus; ++ctu) {
+        const int ctuX = 128 * (ctu % ctuCols), ctuY = 128 * (ctu / ctuCols);
+        for (int t = 0; t < MIP_NUM_TYPES; ++t) {
+            const mip_cu_type_t& ty = MIP_TYPES[t];
+            for (int cu = 0; cu < ty.n; ++cu) {
+                const size_t i = (size_t)ctu * MIP_CUS_PER_CTU + ty.cu_off + cu;
+                char pre[160];
+                const int pl = snprintf(pre, sizeof(pre), "%ld,%d,%s,%d,%d,%d,%d,%d,", poc, ctu, ty.name, ty.w, ty.h, cu,
+                                        ctuX + ty.xs[cu % ty.cols], ctuY + ty.ys[cu / ty.cols]);
+                lb.ensure(256);
+                lb.put(pre, pl);
+                lb.put_int(bm[i]); lb.b[lb.n++] = ',';
+                lb.put_int(bc[i]); lb.b[lb.n++] = '\n';
+            }
+        }
+    }
+}
+
 struct Shared {
     Options opt;
     int W = 0, H = 0, nCtus = 0, filterType = 0;
     const uint16_t* frames = nullptr;
     std::vector<std::vector<int32_t>> keepCost, keepSad, keepSatd;  // per frame, only those that get logged
+    std::vector<std::vector<uint8_t>> keepMode;                     // per frame, with --DecisionsLog
+    std::vector<std::vector<int32_t>> keepBest;
     std::atomic<int> errors{0};
 };
 
@@ -278,8 +335,9 @@ void gpu_worker(Shared* sh, int g, int G) {
     mipb200_config cfg;
     cfg.width = sh->W; cfg.height = sh->H; cfg.device = o.deviceIndex + g;
     cfg.filter_type = sh->filterType; cfg.kernel_idx = o.kernelIdx; cfg.slots = 3;
-    const bool wantLog = !o.noLog;
-    cfg.emit = MIPB200_EMIT_COSTS | (wantLog && !o.compat ? MIPB200_EMIT_SAD_SATD : 0);
+    const bool wantLog = !o.noLog, wantDec = !o.decisionsLog.empty();
+    cfg.emit = (wantLog || !wantDec ? MIPB200_EMIT_COSTS : 0) | (wantLog && !o.compat ? MIPB200_EMIT_SAD_SATD : 0) |
+               (wantDec ? MIPB200_EMIT_DECISIONS : 0);
     mipb200_engine* e = nullptr;
     if (mipb200_create(&e, &cfg) != 0) {
         fprintf(stderr, "[!] ERROR (GPU %d): %s\n", cfg.device, mipb200_last_error());
@@ -295,6 +353,11 @@ void gpu_worker(Shared* sh, int g, int G) {
         if (wantLog && (poc == 0 || o.allFrames)) {   // the reference exports frame 0 only (main.cpp:1268)
             sh->keepCost[poc].assign(r.cost, r.cost + ncost);
             if (r.sad) { sh->keepSad[poc].assign(r.sad, r.sad + ncost); sh->keepSatd[poc].assign(r.satd, r.satd + ncost); }
+        }
+        if (wantDec) {
+            const size_t ncu = (size_t)sh->nCtus * MIP_CUS_PER_CTU;
+            sh->keepMode[poc].assign(r.best_mode, r.best_mode + ncu);
+            sh->keepBest[poc].assign(r.best_cost, r.best_cost + ncu);
         }
         done += G;
         return true;
@@ -358,10 +421,18 @@ int main(int argc, char** argv) {
 
     print_timestamp("START READ SAMPLES .csv");
     std::vector<uint16_t> frames;
-    if (!read_frames_csv(o.input, W, H, o.nFrames, frames)) return 1;
+    if (o.inputFormat == "csv") {
+        if (!read_frames_csv(o.input, W, H, o.nFrames, frames)) return 1;
+    } else if (o.inputFormat == "u16" || o.inputFormat == "yuv420p" || o.inputFormat == "yuv420p10le") {
+        if (!read_frames_binary(o.input, o.inputFormat, W, H, o.nFrames, frames)) return 1;
+    } else {
+        printf("  [!] ERROR: InputFormat %s not supported (csv, u16, yuv420p, yuv420p10le)\n", o.inputFormat.c_str());
+        return 1;
+    }
     print_timestamp("FINISH READ SAMPLES .csv");
     sh.frames = frames.data();
     sh.keepCost.resize(o.nFrames); sh.keepSad.resize(o.nFrames); sh.keepSatd.resize(o.nFrames);
+    sh.keepMode.resize(o.nFrames); sh.keepBest.resize(o.nFrames);
 
     // ---- timed window: first upload -> last result resident on the host (main.cpp:566-569, 1247-1250)
     print_timestamp("START WRITE SAMPLES MEMOBJ");
@@ -386,6 +457,17 @@ int main(int argc, char** argv) {
         for (int poc = 0; poc < (o.allFrames ? o.nFrames : 1); ++poc)
             write_frame_log(lb, poc, o.allFrames, sh.keepCost[poc].data(), sh.keepSad[poc].empty() ? nullptr : sh.keepSad[poc].data(),
                             sh.keepSatd[poc].empty() ? nullptr : sh.keepSatd[poc].data(), sh.nCtus, W, o.compat);
+        lb.flush();
+        fclose(f);
+    }
+
+    if (!o.decisionsLog.empty()) {
+        FILE* f = fopen(o.decisionsLog.c_str(), "w");
+        if (!f) { perror("error while opening the decisions log"); return 1; }
+        LogBuf lb(f);
+        const char* hdr = "POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost\n";
+        lb.put(hdr, strlen(hdr));
+        for (int poc = 0; poc < o.nFrames; ++poc) write_decisions(lb, poc, sh.keepMode[poc].data(), sh.keepBest[poc].data(), sh.nCtus, W);
         lb.flush();
         fclose(f);
     }
