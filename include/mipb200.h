@@ -48,7 +48,8 @@ extern "C" {
  *   5 filterFrame_1d_int_5x5        6 filterFrame_1d_float_5x5
  *   7 filterFrame_2d_int_5x5_quarterCtu  8 filterFrame_2d_float_5x5_quarterCtu */
 typedef struct mipb200_config {
-    int width, height; /* luma size; width % 128 == 0, height % 4 == 0 (main.cpp:289-309) */
+    int width, height; /* luma size; width % 8 == 0, height % 4 == 0 (a superset of main.cpp:289-309; CUs that
+                          cross the right or bottom frame edge are skipped: cost -1) */
     int device;        /* CUDA ordinal == --DeviceIndex (main.cpp:221-228) */
     int filter_type;   /* 0..8, see above (--FilterType, main.cpp:57) */
     int kernel_idx;    /* --KernelIdx (main.cpp:58): 0..4 for 3x3 filters, 0..2 for 5x5 */

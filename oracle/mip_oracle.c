@@ -297,7 +297,9 @@ static void ctu_type_costs(const uint16_t* O, const uint16_t* F, int W, int H, i
         int32_t* c = cost + ty->cost_off + cu * modes;
         int32_t* s1 = sad_o ? sad_o + ty->cost_off + cu * modes : NULL;
         int32_t* s2 = satd_o ? satd_o + ty->cost_off + cu * modes : NULL;
-        if (Y + h > H) {  /* intra.cl:96, 232, 717: skipped by the reference, garbage there */
+        if (Y + h > H || X + w > W) {  /* bottom: intra.cl:96, 232, 717 -- skipped by the reference, garbage there;
+                                        * right: the reference has no x-guards at all (it wraps into the next row for the
+                                        * whitelisted 832x480 / 416x240), so "skipped" is this project's definition */
             for (int m = 0; m < modes; ++m) {
                 c[m] = MIPO_SKIPPED;
                 if (s1) s1[m] = MIPO_SKIPPED;
@@ -326,7 +328,7 @@ static void ctu_type_costs(const uint16_t* O, const uint16_t* F, int W, int H, i
  * sad/satd may be NULL.  threads <= 0 -> all cores. */
 API int mipo_frame_costs(const uint16_t* orig, const uint16_t* ref, int W, int H,
                          int32_t* cost, int32_t* sad, int32_t* satd, int threads) {
-    if (W <= 0 || H <= 0 || W % 128 != 0 || H % 4 != 0) return -1;
+    if (W <= 0 || H <= 0 || W % 4 != 0 || H % 4 != 0) return -1;
     const int cols = (W + 127) / 128, rows = (H + 127) / 128, nctu = cols * rows;
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);

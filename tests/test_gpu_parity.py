@@ -165,3 +165,18 @@ def test_ragged_heights(mip, oracle, shape, ft, kidx):
     bm, bc = oracle.decisions(want)
     _assert_same(got["best_mode"], bm, "best_mode")
     _assert_same(got["best_cost"], bc, "best_cost")
+
+
+@pytest.mark.parametrize("shape", [(240, 416), (480, 832), (64, 8), (72, 136), (128, 248)])
+@pytest.mark.parametrize("ft,kidx", [(0, 0), (8, 2), (1, 4)])
+def test_widths_that_are_not_multiples_of_128(mip, oracle, shape, ft, kidx):
+    """The reference whitelists 832x480 and 416x240 but has no x-guards there; here CUs crossing the right edge are skipped."""
+    from mipb200 import frames, tables as T
+    h, w = shape
+    f = frames.natural_frame(w, h, 17)
+    got = _run(mip, f, ft, kidx, emit=mip.EMIT_COSTS | mip.EMIT_DECISIONS)
+    want = oracle.run_frame(f, ft, kidx)
+    _assert_same(got["cost"], want, f"cost {w}x{h} ft={ft}")
+    bm, bc = oracle.decisions(want)
+    _assert_same(got["best_mode"], bm, "best_mode")
+    assert np.array_equal(got["best_mode"] != 0xFF, T.in_frame_mask(w, h))

@@ -411,9 +411,9 @@ int main(int argc, char** argv) {
             return 0;
         }
     }
-    if (W <= 0 || H <= 0 || W % 128 != 0 || H % 4 != 0) {
+    if (W < 8 || H < 4 || W % 8 != 0 || H % 4 != 0) {
         printf("[!] ERROR: Unsupported resolution %dx%d\n", W, H);
-        printf("Supported resolutions are: any WxH with W %% 128 == 0 and H %% 4 == 0, e.g.\n  3840x2160\n  1920x1080\n  1280x720\n");
+        printf("Supported resolutions are: any WxH with W %% 8 == 0 and H %% 4 == 0, e.g.\n  3840x2160\n  1920x1080\n  1280x720\n  832x480\n  416x240\n");
         return 0;
     }
     if (o.nFrames < 1 || o.numGpus < 1) { printf("  [!] ERROR: FramesToBeEncoded and NumGpus must be positive\n"); return 1; }

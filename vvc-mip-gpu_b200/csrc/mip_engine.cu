@@ -73,8 +73,8 @@ MIPB200_API int mipb200_num_ctus(int w, int h) { return ((w + 127) / 128) * ((h 
 
 static int check_cfg(const mipb200_config* c) {
     if (!c) return fail(MIPB200_EINVAL, "config is NULL");
-    if (c->width <= 0 || c->height <= 0 || c->width % 128 != 0 || c->height % 4 != 0)
-        return fail(MIPB200_EINVAL, "unsupported resolution %dx%d (need width %% 128 == 0, height %% 4 == 0)", c->width, c->height);
+    if (c->width < 8 || c->height < 4 || c->width % 8 != 0 || c->height % 4 != 0)
+        return fail(MIPB200_EINVAL, "unsupported resolution %dx%d (need width %% 8 == 0, height %% 4 == 0)", c->width, c->height);
     if (c->filter_type < 0 || c->filter_type > 8) return fail(MIPB200_EINVAL, "filter_type %d out of range 0..8", c->filter_type);
     if (c->filter_type > 0) {
         const int nk = c->filter_type >= 5 ? 3 : 5;

@@ -514,7 +514,7 @@ __device__ __forceinline__ void build_ref_tile(uint16_t* s_refT, uint16_t* s_ref
         }
         const int y = tileY + ty, x = ctuX + tx;
         int v = 0;
-        if (x >= 0 && y >= 0 && y < H) {
+        if (x >= 0 && x < W && y >= 0 && y < H) {
             const uint16_t* p = stg + (ty + STG_Y0) * STG_W + (tx + STG_X0);
             if constexpr (!FILTER) {
                 v = *p;
@@ -556,7 +556,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     const int tid = threadIdx.x, lane = tid & 31;
     // chunk-major unit order: CTAs that are resident together work on the same chunk (the same CU
     // shapes, hence the same code) of different CTU halves, which keeps the instruction caches warm
-    const int ctuCols = W >> 7;
+    const int ctuCols = (W + 127) >> 7;
     const int halves = 2 * ctuCols * ((H + 127) >> 7);
     const int chunk = blockIdx.x / halves, hu = blockIdx.x - chunk * halves;
     const int ctu = hu >> 1, half = hu & 1;
@@ -629,7 +629,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const int cuLocal = vcu >> pl2, part = vcu & ((1 << pl2) - 1);
         const int cu = ty.first_cu[half] + cuLocal;
         const int cuX = ty.xs[cu & (ty.cols - 1)], cuY = ty.ys[cu >> ty.cols_log2] - half * TILE_ROWS;
-        const bool active = cuY + ty.h <= rowsValid;
+        const bool active = cuY + ty.h <= rowsValid && ctuX + cuX + ty.w <= W;   // CU fully inside the frame
         int sad = 0, satd = 0;
         if (__any_sync(0xffffffffu, active)) {
             switch (ty.shape) {
@@ -949,7 +949,7 @@ cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, const FilterPara
     CUtensorMap map;
     cudaError_t e = make_frame_map(d_frame, W, H, &map);
     if (e != cudaSuccess) return e;
-    const int nctu = (W >> 7) * ((H + 127) >> 7);
+    const int nctu = ((W + 127) >> 7) * ((H + 127) >> 7);
     mip_cost_kernel<<<nctu * 2 * g_chunks, NT, SM_TOTAL, st>>>(map, fp, W, H, g_chunks, d_cost, d_sad, d_satd, d_best_mode, d_best_cost);
     return cudaGetLastError();
 }

@@ -203,15 +203,15 @@ def num_ctus(width: int, height: int) -> int:
 
 
 def in_frame_mask(width: int, height: int):
-    """bool[nCTU][5380]: CU fully inside the frame (reference intra.cl:96,232,717)."""
+    """bool[nCTU][5380]: CU fully inside the frame (bottom edge: reference intra.cl:96,232,717; right edge: ours)."""
     import numpy as np
 
     cols, rows = ctu_grid(width, height)
     m = np.zeros((cols * rows, CUS_PER_CTU), dtype=bool)
     for ctu in range(cols * rows):
-        y0 = CTU * (ctu // cols)
+        x0, y0 = CTU * (ctu % cols), CTU * (ctu // cols)
         for t in TYPES:
             for cu in range(t.n):
-                _, y = t.pos(cu)
-                m[ctu, CU_OFFSETS[t.idx] + cu] = (y0 + y + t.h) <= height
+                x, y = t.pos(cu)
+                m[ctu, CU_OFFSETS[t.idx] + cu] = (y0 + y + t.h) <= height and (x0 + x + t.w) <= width
     return m
