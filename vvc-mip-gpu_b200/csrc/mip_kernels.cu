@@ -88,7 +88,6 @@ struct DevType {
     uint16_t first_cu[2], n_cu[2];   // CUs of the type that lie in the top / bottom half of the CTU (contiguous in CU order)
     uint8_t parts_log2, pad[3];      // lanes that share one (CU, mode): 4 for 64x64 (a quarter of the strips each), else 1
     uint16_t cu_ord[2];              // ordinal of the type's first CU among all CUs of the top / bottom half
-    uint16_t mg, mg_magic;           // mode groups of 4 per CU (modes / 4) and wt / mg == (wt * mg_magic) >> 16
     uint32_t cost_off, cu_off;
     uint8_t xs[32], ys[32];
 };
@@ -507,7 +506,9 @@ __device__ __forceinline__ void build_ref_tile(uint16_t* s_refT, uint16_t* s_ref
             tx = cc - 1;
             dst = s_refT + slot * RT_STRIDE + 8 + tx;
         } else {
-            const int k = i - NROW, slot = k / 65, rr = k - slot * 65;
+            // slot fastest: neighbouring lanes read the staged tile 4 samples apart in the same row (2-way bank
+            // conflicts); row fastest would walk down a column of the 72-word-pitch staging tile (8-way)
+            const int k = i - NROW, rr = k / RL_SLOTS, slot = k - rr * RL_SLOTS;
             tx = slot == RL_COL0 ? 0 : 4 * slot - 1;
             ty = rr - 1;
             dst = s_refL + slot * RL_STRIDE + 8 + ty;
@@ -618,18 +619,21 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         if (lane == 0) wi = atomicAdd(s_next, 1);
         wi = __shfl_sync(0xffffffffu, wi, 0);
         if (wi >= wcnt) break;
-        // warp task = 8 (virtual) CUs x 4 consecutive modes of one type: lane = 4 * cu + mode
+        // warp task = 32 consecutive (CU, mode) pairs of one type: a warp touches at most 3-4 CUs, so the shared-memory
+        // reads of originals and boundaries are mostly broadcasts (8 CUs x 4 modes per warp measured 60 % more bank conflicts)
         const uint32_t rec = c_work[half][wbeg + wi];
         const int t = rec & 0xff, wt = rec >> 8;
         const DevType& ty = c_types[t];
         const int modes = ty.modes, pl2 = ty.parts_log2;
-        const int cuGroup = (int)(((uint32_t)wt * ty.mg_magic) >> 16), modeGroup = wt - cuGroup * ty.mg;
-        const int mode = modeGroup * 4 + (lane & 3);
-        const int vcu = cuGroup * 8 + (lane >> 2);                 // virtual CU = (CU, strip group) for the 64x64 type
-        const int cuLocal = vcu >> pl2, part = vcu & ((1 << pl2) - 1);
+        const int ntask = (ty.n_cu[half] * modes) << pl2;
+        const int task = wt * 32 + lane;
+        const bool inRange = task < ntask;
+        const int tcl = inRange ? task : ntask - 1;
+        const int part = tcl & ((1 << pl2) - 1), cm = tcl >> pl2;
+        const int cuLocal = (int)(((uint32_t)cm * ty.mode_magic) >> 16), mode = cm - cuLocal * modes;
         const int cu = ty.first_cu[half] + cuLocal;
         const int cuX = ty.xs[cu & (ty.cols - 1)], cuY = ty.ys[cu >> ty.cols_log2] - half * TILE_ROWS;
-        const bool active = cuY + ty.h <= rowsValid && ctuX + cuX + ty.w <= W;   // CU fully inside the frame
+        const bool active = inRange && cuY + ty.h <= rowsValid && ctuX + cuX + ty.w <= W;   // CU fully inside the frame
         int sad = 0, satd = 0;
         if (__any_sync(0xffffffffu, active)) {
             switch (ty.shape) {
@@ -651,12 +655,12 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 case S4x8:   run_task<1, 4, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
                 default:     run_task<0, 4, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
             }
-            if (pl2) {   // lanes l, l^4, l^8, l^12 hold the four strip groups of one (CU, mode)
-                sad += __shfl_xor_sync(0xffffffffu, sad, 4);  satd += __shfl_xor_sync(0xffffffffu, satd, 4);
-                sad += __shfl_xor_sync(0xffffffffu, sad, 8);  satd += __shfl_xor_sync(0xffffffffu, satd, 8);
+            if (pl2) {   // lanes 4k..4k+3 hold the four strip groups of one (CU, mode)
+                sad += __shfl_xor_sync(0xffffffffu, sad, 1);  satd += __shfl_xor_sync(0xffffffffu, satd, 1);
+                sad += __shfl_xor_sync(0xffffffffu, sad, 2);  satd += __shfl_xor_sync(0xffffffffu, satd, 2);
             }
         }
-        if (part == 0) {
+        if (inRange && part == 0) {
             const size_t o = ctuBase + ty.cost_off + cu * modes + mode;
             const int cost = min(2 * sad, satd);            // intra.cl:1166
             if (g_cost) g_cost[o] = active ? cost : -1;
@@ -817,21 +821,15 @@ cudaError_t kernels_init(int chunks) {
             d.n_cu[hf] = (uint16_t)cnt;
             const double mv = s.size_id == 2 ? 700.0 : (s.size_id == 1 ? 200.0 : 120.0);
             const double c = (mv + 11.0 * s.w * s.h + 2.0 * (s.w + s.h) + 60.0) / (1 << d.parts_log2) + (d.parts_log2 ? mv : 0.0);
-            // warp task = 8 virtual CUs x 4 modes; the modes/4 tasks of a CU group are consecutive
-            const int vcus = cnt << d.parts_log2;
-            if (vcus % 8 != 0 || s.modes % 4 != 0) return cudaErrorInvalidValue;
-            d.mg = (uint16_t)(s.modes / 4);
-            d.mg_magic = (uint16_t)((65536 + d.mg - 1) / d.mg);
-            const int nw = (vcus / 8) * d.mg;
-            for (int w = 0; w < nw; ++w)
-                if ((int)(((uint32_t)w * d.mg_magic) >> 16) != w / d.mg) return cudaErrorInvalidValue;
+            const int per_cu = s.modes << d.parts_log2, ntask = cnt * per_cu;
+            const int nw = (ntask + 31) / 32;
             d.cu_ord[hf] = (uint16_t)ord_total[hf];
             for (int w = 0; w < nw; ++w) {
                 work[hf].push_back((uint32_t)t | ((uint32_t)w << 8));
                 wcost[hf].push_back(c);
-                const bool group_done = (w + 1) % d.mg == 0;       // all modes of 8 virtual CUs evaluated
-                cut_ok[hf].push_back(group_done);
-                ord_after[hf].push_back(ord_total[hf] + ((((w + 1) / d.mg) * 8) >> d.parts_log2));
+                const int done = std::min(ntask, 32 * (w + 1));
+                cut_ok[hf].push_back(done % per_cu == 0);
+                ord_after[hf].push_back(ord_total[hf] + done / per_cu);
             }
             for (int k = 0; k < cnt; ++k) ord2cu[hf][ord_total[hf] + k] = (uint16_t)(s.cu_off + d.first_cu[hf] + k);
             ord_total[hf] += cnt;
