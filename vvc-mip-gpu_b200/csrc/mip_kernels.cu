@@ -55,10 +55,17 @@ constexpr int RL_STRIDE = 72, RL_SLOTS = 34, RL_COL0 = 33;    // column slot: [y
 constexpr int TILE_ROWS = 64;            // a CTA works on the top or bottom half of a CTU
 constexpr int RED_WORDS = 32;           // packed reduced-prediction words per thread (64 samples)
 
-constexpr int M2_OFF = 0, M2_STRIDE = 520;            // 6 x (64 x 8 B), +8 B pad against bank aliasing
-constexpr int M1_OFF = M2_OFF + 6 * M2_STRIDE, M1_STRIDE = 136;   // 8 x (16 x 8 B) + 8
-constexpr int M0_OFF = M1_OFF + 8 * M1_STRIDE, M0_STRIDE = 68;    // 16 x (16 x 4 B) + 4
-constexpr int MAT_BYTES = M0_OFF + 16 * M0_STRIDE;    // 5296
+// Every matrix is kept twice: as is, and with its rows permuted by the transposition p = y*r + x -> x*r + y, so that
+// transposed modes read row "output position" like the others.  The lanes of a warp hold different modes, i.e. read
+// different matrices at the same row: the per-matrix pads spread the matrices over distinct banks, and each permuted
+// copy starts a whole number of bank groups after the plain one (48 B / 64 B / 64 B modulo 128), so plain and transposed
+// lanes never collide either.
+constexpr int M2_STRIDE = 520, M1_STRIDE = 136, M0_STRIDE = 68;   // 64x8 B + 8, 16x8 B + 8, 16x4 B + 4
+constexpr int M2_OFF = 0, M2T_OFF = M2_OFF + 6 * M2_STRIDE;       // 3120 = 24*128 + 48
+constexpr int M1_OFF = M2T_OFF + 6 * M2_STRIDE, M1T_OFF = M1_OFF + 8 * M1_STRIDE;    // +1088 = 8*128 + 64
+constexpr int M0_OFF = M1T_OFF + 8 * M1_STRIDE, M0T_OFF = M0_OFF + 16 * M0_STRIDE;   // +1088
+constexpr int MAT_BYTES = M0T_OFF + 16 * M0_STRIDE;   // 10592
+static_assert((M2T_OFF - M2_OFF) % 128 == 48 && (M1T_OFF - M1_OFF) % 128 == 64 && (M0T_OFF - M0_OFF) % 128 == 64, "bank phases");
 
 constexpr int SM_RED = 0;                                      // first: the TMA box lands here (128-byte aligned)
 constexpr int SM_RED_BYTES = RED_WORDS * NT * 4;               // 49152 at NT = 384
@@ -276,18 +283,16 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 #pragma unroll
         for (int k = 0; k < B; ++k) ipk[k] = (in[2 * k] & 0xffff) | (in[2 * k + 1] << 16);
     }
-    // matrix row p of output position (a, b): p = a*R + b, or b*R + a for transposed modes
-    const int stepB = tr ? R : 1, stepA = tr ? 1 : R;
 
     if constexpr (SID == 0) {
         // 4x4: the reduced prediction is the prediction (intra.cl:726-727, 934-935)
-        const uint8_t* mb = c.s_mat + M0_OFF + mat * M0_STRIDE;
+        const uint8_t* mb = c.s_mat + (tr ? M0T_OFF : M0_OFF) + mat * M0_STRIDE;   // row = output position, also for transposed modes
         int p[16];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const int cw = *reinterpret_cast<const int*>(mb + (a * stepA + b * stepB) * 4);
+                const int cw = *reinterpret_cast<const int*>(mb + (a * 4 + b) * 4);
                 int acc = 32;
                 acc = __dp2a_lo(ipk[0], cw, acc);
                 acc = __dp2a_hi(ipk[1], cw, acc);
@@ -305,7 +310,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
         return;
     } else {
         // ---- A.3 matrix-vector product -> private scratch column, two samples per word
-        const uint8_t* mb = c.s_mat + (SID == 2 ? M2_OFF + mat * M2_STRIDE : M1_OFF + mat * M1_STRIDE);
+        const uint8_t* mb = c.s_mat + (SID == 2 ? (tr ? M2T_OFF : M2_OFF) + mat * M2_STRIDE : (tr ? M1T_OFF : M1_OFF) + mat * M1_STRIDE);
 #pragma unroll 1
         for (int a = 0; a < R; ++a) {
 #pragma unroll
@@ -313,7 +318,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
                 int v[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int2 cw = *reinterpret_cast<const int2*>(mb + (a * stepA + (b + e) * stepB) * 8);
+                    const int2 cw = *reinterpret_cast<const int2*>(mb + (a * R + b + e) * 8);
                     int acc = 32;
                     acc = __dp2a_lo(ipk[0], cw.x, acc);
                     acc = __dp2a_hi(ipk[1], cw.x, acc);
@@ -666,8 +671,17 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             if (g_cost) g_cost[o] = active ? cost : -1;
             if (g_sad) g_sad[o] = active ? sad : -1;
             if (g_satd) g_satd[o] = active ? satd : -1;
-            // decision = argmin over the CU's modes, lowest mode wins ties: min of (cost << 6 | mode), cost < 2^24
-            if (g_best_mode && active) atomicMin(&s_dec[ty.cu_ord[half] + cuLocal - ordBeg], ((uint32_t)cost << 6) | (uint32_t)mode);
+        }
+        if (g_best_mode) {
+            // decision = argmin over the CU's modes, lowest mode wins ties: min of (cost << 6 | mode), cost < 2^24.
+            // The lanes of one CU are first reduced in registers (MATCH.ANY + REDUX.MIN), then one lane per CU does the
+            // shared-memory atomicMin: 3-4 distinct addresses per warp instead of 32 lanes serialising on them.
+            const bool vote = inRange && part == 0 && active;
+            const unsigned grp = __match_any_sync(0xffffffffu, vote ? cuLocal : -1 - lane);
+            if (vote) {
+                const uint32_t best = __reduce_min_sync(grp, ((uint32_t)min(2 * sad, satd) << 6) | (uint32_t)mode);
+                if (lane == __ffs(grp) - 1) atomicMin(&s_dec[ty.cu_ord[half] + cuLocal - ordBeg], best);
+            }
         }
     }
     if (g_best_mode) {
@@ -865,15 +879,28 @@ cudaError_t kernels_init(int chunks) {
     if ((err = cudaMemcpyToSymbol(c_ord2cu, ord2cu, sizeof(ord2cu))) != cudaSuccess) return err;
     // matrices: (coef - 32) as signed bytes in the padded shared-memory layout
     std::vector<uint8_t> mat(MAT_BYTES, 0);
+    auto tpos = [](int p, int r) { return (p % r) * r + p / r; };   // output position of matrix row p in a transposed mode (intra.cl:485-487)
     for (int m = 0; m < 6; ++m)
         for (int p = 0; p < 64; ++p)
-            for (int i = 0; i < 8; ++i) mat[M2_OFF + m * M2_STRIDE + p * 8 + i] = (uint8_t)(int8_t)((int)MIP_MAT_ID2[m][p][i] - 32);
+            for (int i = 0; i < 8; ++i) {
+                const uint8_t v = (uint8_t)(int8_t)((int)MIP_MAT_ID2[m][p][i] - 32);
+                mat[M2_OFF + m * M2_STRIDE + p * 8 + i] = v;
+                mat[M2T_OFF + m * M2_STRIDE + tpos(p, 8) * 8 + i] = v;
+            }
     for (int m = 0; m < 8; ++m)
         for (int p = 0; p < 16; ++p)
-            for (int i = 0; i < 8; ++i) mat[M1_OFF + m * M1_STRIDE + p * 8 + i] = (uint8_t)(int8_t)((int)MIP_MAT_ID1[m][p][i] - 32);
+            for (int i = 0; i < 8; ++i) {
+                const uint8_t v = (uint8_t)(int8_t)((int)MIP_MAT_ID1[m][p][i] - 32);
+                mat[M1_OFF + m * M1_STRIDE + p * 8 + i] = v;
+                mat[M1T_OFF + m * M1_STRIDE + tpos(p, 4) * 8 + i] = v;
+            }
     for (int m = 0; m < 16; ++m)
         for (int p = 0; p < 16; ++p)
-            for (int i = 0; i < 4; ++i) mat[M0_OFF + m * M0_STRIDE + p * 4 + i] = (uint8_t)(int8_t)((int)MIP_MAT_ID0[m][p][i] - 32);
+            for (int i = 0; i < 4; ++i) {
+                const uint8_t v = (uint8_t)(int8_t)((int)MIP_MAT_ID0[m][p][i] - 32);
+                mat[M0_OFF + m * M0_STRIDE + p * 4 + i] = v;
+                mat[M0T_OFF + m * M0_STRIDE + tpos(p, 4) * 4 + i] = v;
+            }
     if ((err = cudaMemcpyToSymbol(g_mat, mat.data(), MAT_BYTES)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(mip_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(mip_cost_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return err;
