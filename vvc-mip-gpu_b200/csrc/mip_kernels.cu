@@ -340,7 +340,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
             for (int k = 0; k < 4; ++k) prev[k] = T[(x0 + k) * stT];
             if constexpr (UV >= 4) {
                 constexpr int SH = UV == 4 ? 2 : 3;
-#pragma unroll 2
+#pragma unroll 1
                 for (int j = 0; j < R; ++j) {
                     int cur[4];
                     hor_row<R, UH>(c.s_red, j, s, (int)L[(j * UV + UV - 1) * stL], cur);
@@ -367,7 +367,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
                     for (int k = 0; k < 4; ++k) prev[k] = cur[k];
                 }
             } else if constexpr (UV == 2) {
-#pragma unroll 2
+#pragma unroll 1
                 for (int jp = 0; jp < R / 2; ++jp) {
                     int c0[4], c1[4], d[16], o1[4];
                     hor_row<R, UH>(c.s_red, 2 * jp, s, (int)L[(4 * jp + 1) * stL], c0);
