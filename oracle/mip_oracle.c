@@ -205,9 +205,11 @@ static void reduced_prediction(int size_id, int mode, const int* redT, const int
     for (int i = 0; i < 2 * b; ++i) sum += in[i];             /* intra.cl:449-452 */
     const int offset = (1 << 5) - 32 * sum;                   /* intra.cl:454 */
     for (int p = 0; p < r * r; ++p) {
-        const uint8_t* c = size_id == 2 ? MIP_MAT_ID2[mat][p] : (size_id == 1 ? MIP_MAT_ID1[mat][p] : MIP_MAT_ID0[mat][p]);
         int v = offset;
-        for (int i = 0; i < 2 * b; ++i) v += c[i] * in[i];   /* intra.cl:474-479 */
+        for (int i = 0; i < 2 * b; ++i) {                    /* intra.cl:474-479 */
+            const int c = size_id == 2 ? mip_mat_id2(mat, p, i) : (size_id == 1 ? mip_mat_id1(mat, p, i) : mip_mat_id0(mat, p, i));
+            v += c * in[i];
+        }
         v = (v >> 6) + first;                                 /* intra.cl:481 */
         v = iclamp(v, 0, 1023);                               /* intra.cl:482 */
         int x = p % r, y = p / r;

@@ -58,14 +58,15 @@ def test_boundaries_frame_edge_rules(oracle):
 
 
 def _ref_matrices():
+    """MIP matrices parsed from the generated header: one little-endian word per row, tap i = byte i."""
     import re, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     hdr = open(os.path.join(root, "vvc-mip-gpu_b200", "csrc", "mip_matrices.h")).read()
     out = {}
     for name, shape in (("MIP_MAT_ID2", (6, 64, 8)), ("MIP_MAT_ID1", (8, 16, 8)), ("MIP_MAT_ID0", (16, 16, 4))):
-        body = hdr[hdr.index(name):]
-        body = body[body.index("=") + 1: body.index("};")]
-        out[name] = np.array([int(v) for v in re.findall(r"\d+", body)]).reshape(shape)
+        body = hdr[hdr.index(name + "_W"):]
+        words = [int(w, 16) for w in re.findall(r"0x([0-9a-f]+)u", body[body.index("=") + 1: body.index("};")])]
+        out[name] = np.array([(w >> (8 * i)) & 0xFF for w in words for i in range(shape[2])]).reshape(shape)
     return out
 
 

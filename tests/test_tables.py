@@ -112,8 +112,10 @@ def test_matrices_match_reference_mip_matrix_cl():
     spec.loader.exec_module(g)
     mats = g.parse_matrices(REF)
     hdr = open(os.path.join(root, "vvc-mip-gpu_b200", "csrc", "mip_matrices.h")).read()
-    for name, ref_name, k_src, pad in (("MIP_MAT_ID2", "mipMatrix16x16", 7, 1), ("MIP_MAT_ID1", "mipMatrix8x8", 8, 0), ("MIP_MAT_ID0", "mipMatrix4x4", 4, 0)):
-        ours = _ints(_c_array(hdr, "static const uint8_t " + name))
+    for name, ref_name, k_src, pad, nk in (("MIP_MAT_ID2_W", "mipMatrix16x16", 7, 1, 8), ("MIP_MAT_ID1_W", "mipMatrix8x8", 8, 0, 8), ("MIP_MAT_ID0_W", "mipMatrix4x4", 4, 0, 4)):
+        body = hdr[hdr.index(name):]
+        words = [int(w, 16) for w in re.findall(r"0x([0-9a-f]+)u", body[body.index("=") + 1: body.index("};")])]
+        ours = [(w >> (8 * i)) & 0xFF for w in words for i in range(nk)]       # tap i = byte i (little endian)
         (nm, np_, _), vals = mats[ref_name]
         want = []
         for r in range(nm * np_):

@@ -883,21 +883,21 @@ cudaError_t kernels_init(int chunks) {
     for (int m = 0; m < 6; ++m)
         for (int p = 0; p < 64; ++p)
             for (int i = 0; i < 8; ++i) {
-                const uint8_t v = (uint8_t)(int8_t)((int)MIP_MAT_ID2[m][p][i] - 32);
+                const uint8_t v = (uint8_t)(int8_t)(mip_mat_id2(m, p, i) - 32);
                 mat[M2_OFF + m * M2_STRIDE + p * 8 + i] = v;
                 mat[M2T_OFF + m * M2_STRIDE + tpos(p, 8) * 8 + i] = v;
             }
     for (int m = 0; m < 8; ++m)
         for (int p = 0; p < 16; ++p)
             for (int i = 0; i < 8; ++i) {
-                const uint8_t v = (uint8_t)(int8_t)((int)MIP_MAT_ID1[m][p][i] - 32);
+                const uint8_t v = (uint8_t)(int8_t)(mip_mat_id1(m, p, i) - 32);
                 mat[M1_OFF + m * M1_STRIDE + p * 8 + i] = v;
                 mat[M1T_OFF + m * M1_STRIDE + tpos(p, 4) * 8 + i] = v;
             }
     for (int m = 0; m < 16; ++m)
         for (int p = 0; p < 16; ++p)
             for (int i = 0; i < 4; ++i) {
-                const uint8_t v = (uint8_t)(int8_t)((int)MIP_MAT_ID0[m][p][i] - 32);
+                const uint8_t v = (uint8_t)(int8_t)(mip_mat_id0(m, p, i) - 32);
                 mat[M0_OFF + m * M0_STRIDE + p * 4 + i] = v;
                 mat[M0T_OFF + m * M0_STRIDE + tpos(p, 4) * 4 + i] = v;
             }
