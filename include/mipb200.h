@@ -16,6 +16,7 @@
 #ifndef MIPB200_H
 #define MIPB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -24,6 +25,7 @@ extern "C" {
 
 #define MIPB200_COSTS_PER_CTU 97840 /* (CU,mode) pairs per 128x128 CTU, constants.h:1627-1629 */
 #define MIPB200_CUS_PER_CTU 5380    /* CUs per CTU over the 47 CU types, constants.h:568-570 */
+#define MIPB200_TOPK_MAX 12         /* the fewest modes any CU has (sizeId 2: 2 x 6 matrices) */
 #define MIPB200_SKIPPED (-1)        /* cost of a CU that is not fully inside the frame
                                        (the reference leaves garbage there: intra.cl:96,232,717) */
 
@@ -55,6 +57,12 @@ typedef struct mipb200_config {
     int kernel_idx;    /* --KernelIdx (main.cpp:58): 0..4 for 3x3 filters, 0..2 for 5x5 */
     int slots;         /* frames in flight (>= 1; the reference has BUFFER_SLOTS 2, intra.cl:12) */
     unsigned emit;     /* MIPB200_EMIT_* bitmask, must not be 0 */
+    int top_k;         /* 0 or 1: best mode only; 2..MIPB200_TOPK_MAX: with MIPB200_EMIT_DECISIONS the result also
+                          carries the k cheapest modes of every CU (a shortlist for the encoder's RD search) */
+    int bit_depth;     /* 0 or 10: the reference's hard-wired 10-bit pipeline (default sample 512 and clamp 1023:
+                          intra.cl:61, 446, 482); 8 or 12 scale those constants to 1 << (bits - 1) and (1 << bits) - 1.
+                          Samples must be < 1 << bits.  8-bit content run "as is" through the 10-bit pipeline, which is
+                          what the reference does with it, is bit_depth 10. */
 } mipb200_config;
 
 typedef struct mipb200_engine mipb200_engine;
@@ -71,6 +79,9 @@ typedef struct mipb200_result {
     const uint8_t* best_mode; /* [n_ctus][5380]; argmin over modes, lowest wins ties; 0xFF if skipped */
     const int32_t* best_cost; /* [n_ctus][5380] */
     float gpu_ms;             /* device time of this frame's kernels (CUDA events) */
+    int top_k;                /* entries per CU in the two arrays below (0 when not requested) */
+    const uint8_t* topk_mode; /* [n_ctus][5380][top_k]; ascending (cost, mode); 0xFF if skipped */
+    const int32_t* topk_cost; /* [n_ctus][5380][top_k] */
 } mipb200_result;
 
 /* Replaces the OpenCL platform/context/queue/buffer/program setup, main.cpp:87-315, 408-549. */
@@ -116,8 +127,26 @@ int mipb200_filter_device(mipb200_engine* e, const uint16_t* d_frame, uint16_t* 
 int mipb200_decide_device(mipb200_engine* e, const int32_t* d_cost, uint8_t* d_best_mode,
                           int32_t* d_best_cost, void* stream);
 
+/* The k (1..MIPB200_TOPK_MAX) cheapest modes of every CU of an existing cost table (device pointers, d_cost 16-byte
+ * aligned): d_modes [nCTU][5380][k] uint8 and d_costs [nCTU][5380][k] int32 in ascending (cost, mode) order, i.e.
+ * entry 0 equals mipb200_decide_device()'s answer.  No reference counterpart: the reference stops at the cost log
+ * (main_aux_functions.h:735-798) and leaves the ranking to the consumer. */
+int mipb200_topk_device(mipb200_engine* e, const int32_t* d_cost, int k, uint8_t* d_modes, int32_t* d_costs, void* stream);
+
 /* Number of this library's kernels launched so far on this engine (bench.py: gpu_launches). */
 long long mipb200_kernel_launches(const mipb200_engine* e);
+
+/* Page-lock / release a host range the caller owns (cudaHostRegister), so that mipb200_submit() DMAs frames from
+ * it in place instead of staging them through the slot's pinned buffer.  The reference uploads from pageable
+ * memory (clEnqueueWriteBuffer from a malloc'd array, main.cpp:580-588, 886-898).  Needs a CUDA device. */
+int mipb200_pin_host(void* ptr, size_t bytes);
+int mipb200_unpin_host(void* ptr);
+
+/* Energy counter of the board behind CUDA ordinal `device`, in millijoules since the driver was loaded (NVML,
+ * loaded at run time; MIPB200_ENODEV if NVML or the counter is unavailable).  Read it before and after a run to get
+ * joules per frame -- what the reference obtains by integrating an nvidia-smi power trace over the stage stamps
+ * (powerTracer_NVIDIA.py:9, computeEnergy_NVIDIA.py:44-96). */
+int mipb200_device_energy_mj(int device, unsigned long long* millijoules);
 
 /* Block until everything enqueued on the engine's streams has finished. */
 int mipb200_sync(mipb200_engine* e);

@@ -46,6 +46,16 @@
 #define MIPO_SKIPPED (-1)
 #define API __attribute__((visibility("default")))
 
+/* Sample bit depth.  The reference hard-wires 10 bits (valueDC 1 << 9 intra.cl:61, 1 << 9 intra.cl:446, clamp to 1023
+ * intra.cl:482); 8 and 12 generalise those three constants the way the VVC specification does (1 << (bitDepth - 1),
+ * (1 << bitDepth) - 1).  Parity with the reference exists only for 10.  Set once before a run; not thread-safe. */
+static int g_bit_depth = 10;
+API int mipo_set_bit_depth(int bits) {
+    if (bits != 8 && bits != 10 && bits != 12) return -1;
+    g_bit_depth = bits;
+    return 0;
+}
+
 static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 static inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
@@ -158,7 +168,7 @@ API int mipo_filter_frame(const uint16_t* frame, int W, int H, int filter_type, 
  * ---------------------------------------------------------------------------------------- */
 static void cu_boundaries(const uint16_t* F, int W, int X, int Y, int w, int h, int b,
                           int* refT, int* refL, int* redT, int* redL) {
-    const int valueDC = 1 << 9; /* intra.cl:61 */
+    const int valueDC = 1 << (g_bit_depth - 1); /* intra.cl:61 */
     for (int i = 0; i < w; ++i) {  /* intra.cl:96-107 */
         if (Y > 0) refT[i] = F[(size_t)(Y - 1) * W + X + i];
         else if (X == 0) refT[i] = valueDC;
@@ -200,7 +210,7 @@ static void reduced_prediction(int size_id, int mode, const int* redT, const int
     }
     const int first = in[0];
     for (int i = 0; i < 2 * b; ++i) in[i] -= first;          /* intra.cl:445 */
-    in[0] = (size_id == 2) ? 0 : (1 << 9) - first;            /* intra.cl:446 */
+    in[0] = (size_id == 2) ? 0 : (1 << (g_bit_depth - 1)) - first; /* intra.cl:446 */
     int sum = 0;
     for (int i = 0; i < 2 * b; ++i) sum += in[i];             /* intra.cl:449-452 */
     const int offset = (1 << 5) - 32 * sum;                   /* intra.cl:454 */
@@ -211,7 +221,7 @@ static void reduced_prediction(int size_id, int mode, const int* redT, const int
             v += c * in[i];
         }
         v = (v >> 6) + first;                                 /* intra.cl:481 */
-        v = iclamp(v, 0, 1023);                               /* intra.cl:482 */
+        v = iclamp(v, 0, (1 << g_bit_depth) - 1);               /* intra.cl:482 */
         int x = p % r, y = p / r;
         red[tr ? (x * r + y) : p] = v;                        /* intra.cl:485-487 */
     }

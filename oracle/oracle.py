@@ -42,6 +42,8 @@ def lib():
         L.mipo_frame_costs.restype = ctypes.c_int
         L.mipo_run_frame.argtypes = [u16p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, i32p, i32p, i32p, ctypes.c_int]
         L.mipo_run_frame.restype = ctypes.c_int
+        L.mipo_set_bit_depth.argtypes = [ctypes.c_int]
+        L.mipo_set_bit_depth.restype = ctypes.c_int
         L.mipo_decisions.argtypes = [i32p, ctypes.c_int, u8p, i32p]
         L.mipo_decisions.restype = None
         L.mipo_satd4x4.argtypes = [ip]
@@ -79,15 +81,21 @@ def filter_frame(frame: np.ndarray, filter_type: int, kernel_idx: int) -> np.nda
     return out
 
 
-def run_frame(frame: np.ndarray, filter_type: int = 0, kernel_idx: int = 0, want_sad_satd: bool = False, threads: int = 0):
-    """-> cost[nCTU, 97840] int32 (and sad, satd when asked)."""
+def run_frame(frame: np.ndarray, filter_type: int = 0, kernel_idx: int = 0, want_sad_satd: bool = False, threads: int = 0,
+              bit_depth: int = 10):
+    """-> cost[nCTU, 97840] int32 (and sad, satd when asked).  bit_depth 10 is the reference; 8 / 12 are the extension."""
     frame = np.ascontiguousarray(frame, dtype=np.uint16)
     h, w = frame.shape
     n = num_ctus(w, h)
     cost = np.empty((n, COSTS_PER_CTU), dtype=np.int32)
     sad = np.empty_like(cost) if want_sad_satd else None
     satd = np.empty_like(cost) if want_sad_satd else None
-    rc = lib().mipo_run_frame(_u16(frame), w, h, filter_type, kernel_idx, _i32(cost), _i32(sad), _i32(satd), threads)
+    if lib().mipo_set_bit_depth(bit_depth) != 0:
+        raise ValueError(f"bit_depth {bit_depth} not in (8, 10, 12)")
+    try:
+        rc = lib().mipo_run_frame(_u16(frame), w, h, filter_type, kernel_idx, _i32(cost), _i32(sad), _i32(satd), threads)
+    finally:
+        lib().mipo_set_bit_depth(10)
     if rc != 0:
         raise ValueError(f"mipo_run_frame rc={rc}")
     return (cost, sad, satd) if want_sad_satd else cost
@@ -100,6 +108,27 @@ def decisions(cost: np.ndarray):
     bc = np.empty((n, CUS_PER_CTU), dtype=np.int32)
     lib().mipo_decisions(_i32(cost), n, bm.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _i32(bc))
     return bm, bc
+
+
+def topk(cost: np.ndarray, k: int):
+    """The k cheapest modes of every CU in ascending (cost, mode) order (stable sort over the mode axis):
+    modes uint8 [n][5380][k] (255 for skipped CUs), costs int32 [n][5380][k].  An extension: the reference stops at the
+    cost log (main_aux_functions.h:735-798); entry 0 is decisions()."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(_HERE), "vvc-mip-gpu_b200"))
+    from mipb200 import tables as T
+    cost = np.ascontiguousarray(cost, dtype=np.int32)
+    n = cost.shape[0]
+    tm = np.empty((n, CUS_PER_CTU, k), dtype=np.uint8)
+    tc = np.empty((n, CUS_PER_CTU, k), dtype=np.int32)
+    for t in T.TYPES:
+        c = cost[:, T.COST_OFFSETS[t.idx]:T.COST_OFFSETS[t.idx + 1]].reshape(n, t.n, t.modes)
+        order = np.argsort(c, axis=2, kind="stable")[:, :, :k]
+        sel = np.take_along_axis(c, order, axis=2)
+        skipped = c[:, :, :1] == -1
+        tm[:, T.CU_OFFSETS[t.idx]:T.CU_OFFSETS[t.idx + 1]] = np.where(skipped, 255, order).astype(np.uint8)
+        tc[:, T.CU_OFFSETS[t.idx]:T.CU_OFFSETS[t.idx + 1]] = np.where(skipped, -1, sel)
+    return tm, tc
 
 
 def satd4x4(diff16) -> int:

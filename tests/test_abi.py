@@ -33,11 +33,12 @@ def test_header_compiles_as_c_and_cxx(tmp_path):
 def test_struct_layout_matches_ctypes(mip, tmp_path):
     import subprocess
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mipb200.h"\nint main(void){ printf("%zu %zu %zu %zu %zu\\n", sizeof(mipb200_config), sizeof(mipb200_result), offsetof(mipb200_result, cost), offsetof(mipb200_result, gpu_ms), offsetof(mipb200_config, emit)); return 0; }\n')
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mipb200.h"\nint main(void){ printf("%zu %zu %zu %zu %zu ", sizeof(mipb200_config), sizeof(mipb200_result), offsetof(mipb200_result, cost), offsetof(mipb200_result, gpu_ms), offsetof(mipb200_config, emit)); printf("%zu %zu %zu %zu\\n", offsetof(mipb200_config, bit_depth), offsetof(mipb200_config, top_k), offsetof(mipb200_result, top_k), offsetof(mipb200_result, topk_cost)); return 0; }\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
-    assert [int(v) for v in out] == [ctypes.sizeof(mip.Config), ctypes.sizeof(mip.Result), mip.Result.cost.offset, mip.Result.gpu_ms.offset, mip.Config.emit.offset]
+    assert [int(v) for v in out] == [ctypes.sizeof(mip.Config), ctypes.sizeof(mip.Result), mip.Result.cost.offset, mip.Result.gpu_ms.offset, mip.Config.emit.offset,
+                                     mip.Config.bit_depth.offset, mip.Config.top_k.offset, mip.Result.top_k.offset, mip.Result.topk_cost.offset]
 
 
 def test_no_gpu_means_loud_failure_not_fallback(mip):

@@ -147,3 +147,41 @@ def test_cli_binary_input_and_decisions_log(mip, oracle, tmp_path):
             got_c = np.array([int(x.split(",")[-1]) for x in rows]).reshape(2, 5380)
             assert np.array_equal(got_m, bm) and np.array_equal(got_c, bc)
             assert rows[0].startswith(f"{poc},0,ALL_AL_64x64,64,64,0,0,0,") and rows[5380].startswith(f"{poc},1,ALL_AL_64x64,64,64,0,128,0,")
+
+
+@pytest.mark.gpu
+def test_cli_topk_energy_and_stage_stamps(mip, oracle, tmp_path):
+    """--TopK adds ModeN,CostN columns in (cost, mode) order; --Energy prints joules; the stage stamps that
+    computeEnergy_NVIDIA.py:44-96 parses are all present by default and absent with --StageStamps=0."""
+    from mipb200 import frames
+    fs = [frames.natural_frame(256, 128, 90 + i) for i in range(2)]
+    raw = tmp_path / "in.u16"
+    np.stack(fs).astype("<u2").tofile(str(raw))
+    dec = tmp_path / "dec.csv"
+    r = _run(mip, "-f", "2", "-s", "256x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", f"--DecisionsLog={dec}", "--TopK=3", "--Energy")
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = open(dec).read().splitlines()
+    assert lines[0] == "POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost,Mode2,Cost2,Mode3,Cost3" and len(lines) - 1 == 2 * 2 * 5380
+    for poc in range(2):
+        tm, tc = oracle.topk(oracle.run_frame(fs[poc]), 3)
+        rows = np.array([[int(v) for v in x.split(",")[-6:]] for x in lines[1 + poc * 10760: 1 + (poc + 1) * 10760]]).reshape(2, 5380, 3, 2)
+        assert np.array_equal(rows[..., 0], tm) and np.array_equal(rows[..., 1], tc)
+    for stamp in ("STARTED HOST", "START WRITE SAMPLES MEMOBJ", "FINISH WRITE SAMPLES MEMOBJ", "START ENQUEUE initBoundaries",
+                  "FINISH ENQUEUE initBoundaries", "START ENQUEUE reducedPred", "FINISH ENQUEUE reducedPred",
+                  "START ENQUEUE upsamplePred_SIZEID=2", "FINISH ENQUEUE upsamplePred_SIZEID=2", "START ENQUEUE upsamplePred_SIZEID=1",
+                  "FINISH ENQUEUE upsamplePred_SIZEID=1", "START ENQUEUE upsamplePred_SIZEID=0", "FINISH ENQUEUE upsamplePred_SIZEID=0",
+                  "START READ DISTORTION", "FINISH READ DISTORTION"):
+        hits = [ln for ln in r.stdout.splitlines() if ln.startswith(stamp + " @ ")]
+        assert hits, stamp
+        import re
+        assert re.fullmatch(r".* @ \d\d:\d\d:\d\d\.\d\d\d", hits[-1]), hits[-1]      # "%H:%M:%S.%f" of the energy script
+    assert ("Energy per frame (J)," in r.stdout) or ("Energy counter unavailable" in r.stdout)
+    r = _run(mip, "-f", "2", "-s", "256x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", f"--DecisionsLog={dec}", "--StageStamps=0")
+    assert r.returncode == 0 and "START ENQUEUE" not in r.stdout and "STARTED HOST" in r.stdout
+
+
+def test_topk_argument_checks(mip, tmp_path):
+    r = _run(mip, "-f", "1", "-s", "128x128", "-o", "x.u16", "--TopK=3")
+    assert r.returncode == 1 and "TopK needs --DecisionsLog" in r.stdout
+    r = _run(mip, "-f", "1", "-s", "128x128", "-o", "x.u16", "--TopK=40", "--DecisionsLog=d.csv")
+    assert r.returncode == 1 and "TopK must be in 1..12" in r.stdout

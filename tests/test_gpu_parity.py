@@ -121,6 +121,88 @@ def test_device_resident_path(mip, oracle):
         _assert_same(d_bc2.cpu().numpy(), bc, "decide_device best_cost")
 
 
+@pytest.mark.parametrize("k", [1, 3, 12])
+def test_topk_shortlist(mip, oracle, k):
+    """k cheapest modes per CU in (cost, mode) order: the engine's result ring and the device entry point vs a stable sort
+    of the oracle's table; ties (flat frame: every mode of a CU costs the same) must come out in mode order."""
+    import torch
+    from mipb200 import frames
+    for f, ft in ((frames.natural_frame(256, 136, 31), 0), (np.full((128, 128), 700, np.uint16), 0), (frames.noise_frame(384, 128, 5), 7)):
+        h, w = f.shape
+        want_cost = oracle.run_frame(f, ft, 1)
+        tm, tc = oracle.topk(want_cost, k)
+        with mip.Engine(w, h, filter_type=ft, kernel_idx=1, emit=mip.EMIT_DECISIONS, top_k=k) as eng:
+            r = eng.run(f)
+            assert r.cost is None
+            bm, bc = oracle.decisions(want_cost)
+            _assert_same(r.best_mode, bm, "best_mode")
+            _assert_same(r.best_cost, bc, "best_cost")
+            if k > 1:
+                assert r.top_k == k
+                _assert_same(r.topk_mode, tm, "topk_mode")
+                _assert_same(r.topk_cost, tc, "topk_cost")
+            else:
+                assert r.top_k == 0 and r.topk_mode is None
+            d_cost = torch.from_numpy(want_cost).cuda()
+            d_m = torch.zeros((eng.n_ctus, mip.CUS_PER_CTU, k), dtype=torch.uint8, device="cuda")
+            d_c = torch.zeros((eng.n_ctus, mip.CUS_PER_CTU, k), dtype=torch.int32, device="cuda")
+            st = torch.cuda.Stream()
+            torch.cuda.synchronize()
+            eng.topk_device(d_cost.data_ptr(), k, d_m.data_ptr(), d_c.data_ptr(), stream=st.cuda_stream)
+            st.synchronize()
+            _assert_same(d_m.cpu().numpy(), tm, "topk_device modes")
+            _assert_same(d_c.cpu().numpy(), tc, "topk_device costs")
+    with pytest.raises(mip.MipError):
+        mip.Engine(128, 128, emit=mip.EMIT_COSTS, top_k=4)        # a shortlist needs EMIT_DECISIONS
+    with pytest.raises(mip.MipError):
+        mip.Engine(128, 128, emit=mip.EMIT_DECISIONS, top_k=13)
+
+
+@pytest.mark.parametrize("bits", [8, 12])
+def test_other_bit_depths(mip, oracle, bits):
+    """8- and 12-bit pipelines (default sample 1 << (bits - 1), clamp (1 << bits) - 1): an extension of the reference's
+    hard-wired 10 bits, checked against the oracle with the same generalisation; incl. saturated frames and a filter."""
+    from mipb200 import frames
+    top = (1 << bits) - 1
+    cases = [(frames.noise_frame(256, 136, 3, bits=bits), 0, 0), (frames.natural_frame(384, 128, 4, bits=bits), 8, 2),
+             (np.full((128, 136), top, np.uint16), 0, 0), (frames.noise_frame(136, 64, 9, bits=bits), 1, 4)]
+    chk = np.indices((128, 128)).sum(axis=0) % 2 * top                        # 1-px checkerboard 0 / max
+    cases.append((chk.astype(np.uint16), 3, 1))
+    for f, ft, kidx in cases:
+        h, w = f.shape
+        assert int(f.max()) <= top
+        want = oracle.run_frame(f, ft, kidx, want_sad_satd=True, bit_depth=bits)
+        with mip.Engine(w, h, filter_type=ft, kernel_idx=kidx, emit=mip.EMIT_COSTS | mip.EMIT_SAD_SATD | mip.EMIT_DECISIONS,
+                        bit_depth=bits) as eng:
+            r = eng.run(f)
+            _assert_same(r.cost, want[0], f"{bits}-bit cost")
+            _assert_same(r.sad, want[1], f"{bits}-bit sad")
+            _assert_same(r.satd, want[2], f"{bits}-bit satd")
+            bm, bc = oracle.decisions(want[0])
+            _assert_same(r.best_mode, bm, f"{bits}-bit best_mode")
+            _assert_same(r.best_cost, bc, f"{bits}-bit best_cost")
+    if bits == 12:   # the depth matters: the same 12-bit frame through the 10-bit pipeline clamps differently
+        f = cases[0][0]
+        assert not np.array_equal(oracle.run_frame(f, bit_depth=12), oracle.run_frame(f, bit_depth=10))
+    with pytest.raises(mip.MipError):
+        mip.Engine(128, 128, bit_depth=9)
+
+
+def test_energy_counter(mip):
+    """NVML energy counter through the ABI: monotonic, and it moves while the GPU works."""
+    from mipb200 import frames
+    try:
+        e0 = mip.device_energy_mj(0)
+    except mip.MipError as ex:
+        pytest.skip(f"no NVML energy counter on this box: {ex}")
+    f = frames.natural_frame(1920, 1080, 1)
+    with mip.Engine(1920, 1080, emit=mip.EMIT_DECISIONS) as eng:
+        for _ in range(200):
+            eng.run(f)
+    e1 = mip.device_energy_mj(0)
+    assert e1 > e0
+
+
 def test_errors(mip):
     with pytest.raises(mip.MipError):
         mip.Engine(250, 128)

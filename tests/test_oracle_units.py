@@ -187,3 +187,22 @@ def test_skipped_cus_and_decisions(oracle):
 def test_thread_count_does_not_change_results(oracle):
     f = frames.natural_frame(256, 128, 8)
     assert np.array_equal(oracle.run_frame(f, 5, 2, threads=1), oracle.run_frame(f, 5, 2, threads=4))
+
+
+def test_bit_depth_generalisation(oracle):
+    """bit_depth only moves the three constants the reference hard-wires (intra.cl:61, 446, 482): 10 is the default; a
+    flat frame predicts itself at any depth; at 8 / 12 bits the first CU's default boundary sample is 128 / 2048."""
+    from mipb200 import frames
+    f = frames.noise_frame(128, 128, 11, bits=8)
+    assert np.array_equal(oracle.run_frame(f), oracle.run_frame(f, bit_depth=10))
+    with pytest.raises(ValueError):
+        oracle.run_frame(f, bit_depth=9)
+    for bits in (8, 12):
+        flat = np.full((128, 128), 1 << (bits - 1), np.uint16)              # equals the default sample: every boundary is flat
+        assert not oracle.run_frame(flat, bit_depth=bits).any()
+        assert oracle.run_frame(flat, bit_depth=10).any() == (bits != 10)
+    hi = np.full((128, 128), 4095, np.uint16)
+    c12 = oracle.run_frame(hi, bit_depth=12)
+    c10 = oracle.run_frame(hi, bit_depth=10)
+    assert c12[0, 0] < c10[0, 0]                                              # 10-bit clamp at 1023 cannot reach 4095
+    assert not np.array_equal(oracle.run_frame(f, bit_depth=8), oracle.run_frame(f, bit_depth=10))

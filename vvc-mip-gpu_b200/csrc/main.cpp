@@ -53,14 +53,18 @@ struct Options {
     int kernelIdx = 0;     bool kernelSet = false;
     int useAlt = USE_ALTERNATIVE_SAMPLES;
     int numGpus = 1;
+    int topK = 0;
+    int bitDepth = 10;
+    int stageStamps = -1;   // -1: follow TRACE_POWER when one GPU is used
     std::string inputFormat = "csv", decisionsLog;
-    bool allFrames = false, compat = false, noLog = false, help = false;
+    bool allFrames = false, compat = false, noLog = false, help = false, energy = false;
 };
 
 const char* kLongOpts[] = {"help", "DeviceIndex", "FramesToBeEncoded", "Resolution", "OriginalFrames", "OutputPreffix",
                            "FilterType", "KernelIdx", "UseAlternativeSamples", "NumGpus", "AllFrames", "Compat", "NoLog",
-                           "InputFormat", "DecisionsLog"};
-const bool kTakesValue[] = {false, true, true, true, true, true, true, true, true, true, false, false, false, true, true};
+                           "InputFormat", "DecisionsLog", "TopK", "Energy", "StageStamps", "BitDepth"};
+const bool kTakesValue[] = {false, true, true, true, true, true, true, true, true, true, false, false, false, true, true,
+                            true, false, true, true};
 constexpr int kNumOpts = sizeof(kLongOpts) / sizeof(kLongOpts[0]);
 
 void print_help() {
@@ -77,7 +81,11 @@ void print_help() {
            "  --NumGpus arg (=1)             shard frames over this many GPUs\n"
            "  --AllFrames --Compat --NoLog   log every frame / zero SAD,SATD columns / no text log\n"
            "  --InputFormat arg (=csv)       csv | u16 (raw little-endian luma) | yuv420p | yuv420p10le\n"
-           "  --DecisionsLog arg             write POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost for every frame\n");
+           "  --DecisionsLog arg             write POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost for every frame\n"
+           "  --TopK arg (=1)                with --DecisionsLog: the k cheapest modes per CU (adds Mode2,Cost2,... columns)\n"
+           "  --Energy                       report joules per frame from the board's NVML energy counter\n"
+           "  --BitDepth arg (=10)           8 | 10 | 12; 10 is the reference's pipeline (also for 8-bit content taken as is)\n"
+           "  --StageStamps arg              0|1, the reference's per-frame START/FINISH stage stamps (TRACE_POWER)\n");
 }
 
 // resolves a (possibly abbreviated) long option; -1 unknown, -2 ambiguous
@@ -150,6 +158,10 @@ bool parse_args(int argc, char** argv, Options& o) {
             case 12: o.noLog = true; break;
             case 13: o.inputFormat = val; break;
             case 14: o.decisionsLog = val; break;
+            case 15: ok = to_int(val, &o.topK); break;
+            case 16: o.energy = true; break;
+            case 17: ok = to_int(val, &o.stageStamps); break;
+            case 18: ok = to_int(val, &o.bitDepth); break;
         }
         if (!ok) { fprintf(stderr, "the argument ('%s') for option '--%s' is invalid\n", val.c_str(), kLongOpts[opt]); return false; }
     }
@@ -298,22 +310,27 @@ void write_frame_log(LogBuf& lb, long poc, bool withPoc, const int32_t* cost, co
     }
 }
 
-// per-CU decisions of one frame: POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost (skipped CUs: 255,-1)
-void write_decisions(LogBuf& lb, long poc, const uint8_t* bm, const int32_t* bc, int nCtus, int W) {
+// per-CU decisions of one frame: POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost[,Mode2,Cost2,...] (skipped CUs: 255,-1)
+// bm/bc hold k entries per CU in ascending (cost, mode) order.
+void write_decisions(LogBuf& lb, long poc, const uint8_t* bm, const int32_t* bc, int k, int nCtus, int W) {
     const int ctuCols = (W + 127) / 128;
     for (int ctu = 0; ctu < nCtus; ++ctu) {
         const int ctuX = 128 * (ctu % ctuCols), ctuY = 128 * (ctu / ctuCols);
         for (int t = 0; t < MIP_NUM_TYPES; ++t) {
             const mip_cu_type_t& ty = MIP_TYPES[t];
             for (int cu = 0; cu < ty.n; ++cu) {
-                const size_t i = (size_t)ctu * MIP_CUS_PER_CTU + ty.cu_off + cu;
+                const size_t i = ((size_t)ctu * MIP_CUS_PER_CTU + ty.cu_off + cu) * k;
                 char pre[160];
-                const int pl = snprintf(pre, sizeof(pre), "%ld,%d,%s,%d,%d,%d,%d,%d,", poc, ctu, ty.name, ty.w, ty.h, cu,
+                const int pl = snprintf(pre, sizeof(pre), "%ld,%d,%s,%d,%d,%d,%d,%d", poc, ctu, ty.name, ty.w, ty.h, cu,
                                         ctuX + ty.xs[cu % ty.cols], ctuY + ty.ys[cu / ty.cols]);
-                lb.ensure(256);
+                lb.ensure(512);
                 lb.put(pre, pl);
-                lb.put_int(bm[i]); lb.b[lb.n++] = ',';
-                lb.put_int(bc[i]); lb.b[lb.n++] = '\n';
+                for (int j = 0; j < k; ++j) {
+                    lb.b[lb.n++] = ',';
+                    lb.put_int(bm[i + j]); lb.b[lb.n++] = ',';
+                    lb.put_int(bc[i + j]);
+                }
+                lb.b[lb.n++] = '\n';
             }
         }
     }
@@ -327,14 +344,18 @@ struct Shared {
     std::vector<std::vector<uint8_t>> keepMode;                     // per frame, with --DecisionsLog
     std::vector<std::vector<int32_t>> keepBest;
     std::atomic<int> errors{0};
+    bool stamps = false;
 };
 
-// one host thread per GPU: frames poc = g, g+G, g+2G, ...
-void gpu_worker(Shared* sh, int g, int G) {
+// Engine of GPU g: context, streams, pinned rings, tables.  Runs before the timed window, like the reference's
+// platform / queue / buffer / program setup (main.cpp:87-549).
+mipb200_engine* create_engine(Shared* sh, int g, mipb200_config* cfg_out) {
     const Options& o = sh->opt;
     mipb200_config cfg;
     cfg.width = sh->W; cfg.height = sh->H; cfg.device = o.deviceIndex + g;
     cfg.filter_type = sh->filterType; cfg.kernel_idx = o.kernelIdx; cfg.slots = 3;
+    cfg.top_k = o.topK > 1 ? o.topK : 0;
+    cfg.bit_depth = o.bitDepth;
     const bool wantLog = !o.noLog, wantDec = !o.decisionsLog.empty();
     cfg.emit = (wantLog || !wantDec ? MIPB200_EMIT_COSTS : 0) | (wantLog && !o.compat ? MIPB200_EMIT_SAD_SATD : 0) |
                (wantDec ? MIPB200_EMIT_DECISIONS : 0);
@@ -342,8 +363,16 @@ void gpu_worker(Shared* sh, int g, int G) {
     if (mipb200_create(&e, &cfg) != 0) {
         fprintf(stderr, "[!] ERROR (GPU %d): %s\n", cfg.device, mipb200_last_error());
         sh->errors++;
-        return;
+        return nullptr;
     }
+    *cfg_out = cfg;
+    return e;
+}
+
+// one host thread per GPU: frames poc = g, g+G, g+2G, ...
+void gpu_worker(Shared* sh, mipb200_engine* e, mipb200_config cfg, int g, int G) {
+    const Options& o = sh->opt;
+    const bool wantLog = !o.noLog, wantDec = !o.decisionsLog.empty();
     const size_t fpx = (size_t)sh->W * sh->H, ncost = (size_t)sh->nCtus * MIP_COSTS_PER_CTU;
     int next = g, done = g;
     auto collect_one = [&]() -> bool {
@@ -355,9 +384,11 @@ void gpu_worker(Shared* sh, int g, int G) {
             if (r.sad) { sh->keepSad[poc].assign(r.sad, r.sad + ncost); sh->keepSatd[poc].assign(r.satd, r.satd + ncost); }
         }
         if (wantDec) {
-            const size_t ncu = (size_t)sh->nCtus * MIP_CUS_PER_CTU;
-            sh->keepMode[poc].assign(r.best_mode, r.best_mode + ncu);
-            sh->keepBest[poc].assign(r.best_cost, r.best_cost + ncu);
+            const size_t ncu = (size_t)sh->nCtus * MIP_CUS_PER_CTU * (r.top_k ? r.top_k : 1);
+            const uint8_t* bm = r.top_k ? r.topk_mode : r.best_mode;
+            const int32_t* bc = r.top_k ? r.topk_cost : r.best_cost;
+            sh->keepMode[poc].assign(bm, bm + ncu);
+            sh->keepBest[poc].assign(bc, bc + ncu);
         }
         done += G;
         return true;
@@ -365,17 +396,38 @@ void gpu_worker(Shared* sh, int g, int G) {
     while (done < o.nFrames) {
         while (next < o.nFrames && mipb200_in_flight(e) < cfg.slots) {
             if (G == 1) printf("Current frame %d\n", next);
-            if (mipb200_submit(e, sh->frames + fpx * next, next) != 0) {
+            if (sh->stamps) {
+                // The reference stamps every stage's enqueue (main.cpp:738-1216); here one fused kernel is every stage, so
+                // all stamps bracket the single asynchronous submit.  computeEnergy_NVIDIA.py:44-96 parses these names.
+                if (next > 0) print_timestamp("START WRITE SAMPLES MEMOBJ");
+                if (o.useAlt) print_timestamp("START ENQUEUE filterFrame");
+                print_timestamp("START ENQUEUE initBoundaries");
+                print_timestamp("START ENQUEUE reducedPred");
+                print_timestamp("START ENQUEUE upsamplePred_SIZEID=2");
+                print_timestamp("START ENQUEUE upsamplePred_SIZEID=1");
+                print_timestamp("START ENQUEUE upsamplePred_SIZEID=0");
+            }
+            const int rcs = mipb200_submit(e, sh->frames + fpx * next, next);
+            if (sh->stamps) {
+                print_timestamp("FINISH WRITE SAMPLES MEMOBJ");
+                if (o.useAlt) print_timestamp("FINISH ENQUEUE filterFrame");
+                print_timestamp("FINISH ENQUEUE initBoundaries");
+                print_timestamp("FINISH ENQUEUE reducedPred");
+                print_timestamp("FINISH ENQUEUE upsamplePred_SIZEID=2");
+                print_timestamp("FINISH ENQUEUE upsamplePred_SIZEID=1");
+                print_timestamp("FINISH ENQUEUE upsamplePred_SIZEID=0");
+            }
+            if (rcs != 0) {
                 fprintf(stderr, "[!] ERROR (GPU %d): %s\n", cfg.device, mipb200_last_error());
                 sh->errors++;
-                mipb200_destroy(e);
                 return;
             }
             next += G;
         }
+        if (sh->stamps) print_timestamp("START READ DISTORTION");
         if (!collect_one()) break;
+        if (sh->stamps && done < o.nFrames) print_timestamp("FINISH READ DISTORTION");
     }
-    mipb200_destroy(e);
 }
 
 }  // namespace
@@ -417,6 +469,10 @@ int main(int argc, char** argv) {
         return 0;
     }
     if (o.nFrames < 1 || o.numGpus < 1) { printf("  [!] ERROR: FramesToBeEncoded and NumGpus must be positive\n"); return 1; }
+    if (o.topK < 0 || o.topK > MIPB200_TOPK_MAX) { printf("  [!] ERROR: TopK must be in 1..%d\n", MIPB200_TOPK_MAX); return 1; }
+    if (o.bitDepth != 8 && o.bitDepth != 10 && o.bitDepth != 12) { printf("  [!] ERROR: BitDepth must be 8, 10 or 12\n"); return 1; }
+    if (o.topK > 1 && o.decisionsLog.empty()) { printf("  [!] ERROR: TopK needs --DecisionsLog\n"); return 1; }
+    sh.stamps = o.stageStamps < 0 ? (TRACE_POWER && o.numGpus == 1) : o.stageStamps != 0;
     sh.W = W; sh.H = H; sh.nCtus = mipb200_num_ctus(W, H);
 
     print_timestamp("START READ SAMPLES .csv");
@@ -435,15 +491,41 @@ int main(int argc, char** argv) {
     sh.keepMode.resize(o.nFrames); sh.keepBest.resize(o.nFrames);
 
     // ---- timed window: first upload -> last result resident on the host (main.cpp:566-569, 1247-1250)
+    // ---- set-up (not timed, like the reference's context / buffer / program creation)
+    print_timestamp("START BUILD KERNELS");
+    std::vector<mipb200_engine*> engines(o.numGpus, nullptr);
+    std::vector<mipb200_config> cfgs(o.numGpus);
+    {
+        std::vector<std::thread> th;
+        for (int g = 0; g < o.numGpus; ++g) th.emplace_back([&, g] { engines[g] = create_engine(&sh, g, &cfgs[g]); });
+        for (auto& t : th) t.join();
+    }
+    auto destroy_all = [&] { for (auto* e : engines) mipb200_destroy(e); };
+    if (sh.errors) { destroy_all(); return 1; }
+    // page-lock the frames so that every upload is a DMA from where the samples already are (no staging copy)
+    const bool pinned = mipb200_pin_host(frames.data(), frames.size() * sizeof(uint16_t)) == 0;
+    print_timestamp("FINISH BUILD KERNELS");
+
+    std::vector<unsigned long long> mj0(o.numGpus, 0), mj1(o.numGpus, 0);
+    bool haveEnergy = o.energy;
+    for (int g = 0; g < o.numGpus && haveEnergy; ++g)
+        if (mipb200_device_energy_mj(o.deviceIndex + g, &mj0[g]) != 0) {
+            printf("  [!] Energy counter unavailable: %s\n", mipb200_last_error());
+            haveEnergy = false;
+        }
     print_timestamp("START WRITE SAMPLES MEMOBJ");
     const double t0 = now_ms();
     {
         std::vector<std::thread> th;
-        for (int g = 0; g < o.numGpus; ++g) th.emplace_back(gpu_worker, &sh, g, o.numGpus);
+        for (int g = 0; g < o.numGpus; ++g) th.emplace_back(gpu_worker, &sh, engines[g], cfgs[g], g, o.numGpus);
         for (auto& t : th) t.join();
     }
     const double t1 = now_ms();
     print_timestamp("FINISH READ DISTORTION");
+    for (int g = 0; g < o.numGpus && haveEnergy; ++g)
+        if (mipb200_device_energy_mj(o.deviceIndex + g, &mj1[g]) != 0) haveEnergy = false;
+    destroy_all();
+    if (pinned) mipb200_unpin_host(frames.data());
     if (sh.errors) return 1;
 
     if (!o.noLog) {
@@ -465,9 +547,12 @@ int main(int argc, char** argv) {
         FILE* f = fopen(o.decisionsLog.c_str(), "w");
         if (!f) { perror("error while opening the decisions log"); return 1; }
         LogBuf lb(f);
-        const char* hdr = "POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost\n";
-        lb.put(hdr, strlen(hdr));
-        for (int poc = 0; poc < o.nFrames; ++poc) write_decisions(lb, poc, sh.keepMode[poc].data(), sh.keepBest[poc].data(), sh.nCtus, W);
+        const int k = o.topK > 1 ? o.topK : 1;
+        std::string hdr = "POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost";
+        for (int j = 2; j <= k; ++j) hdr += ",Mode" + std::to_string(j) + ",Cost" + std::to_string(j);
+        hdr += "\n";
+        lb.put(hdr.c_str(), hdr.size());
+        for (int poc = 0; poc < o.nFrames; ++poc) write_decisions(lb, poc, sh.keepMode[poc].data(), sh.keepBest[poc].data(), k, sh.nCtus, W);
         lb.flush();
         fclose(f);
     }
@@ -478,6 +563,16 @@ int main(int argc, char** argv) {
     printf("Elapsed time (ms) from writing samples to reading distortion (%dx), %d\n", o.nFrames, (int)lround(t1 - t0));
     printf("=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=\n\n");
     printf("Throughput: %.1f frames/s on %d GPU(s)\n", o.nFrames * 1e3 / (t1 - t0 > 0 ? t1 - t0 : 1e-3), o.numGpus);
+    if (o.energy && haveEnergy) {
+        // the board's own energy counter over the timed window (the reference integrates an nvidia-smi power trace
+        // between the same two stamps, computeEnergy_NVIDIA.py:98-140)
+        double joules = 0;
+        for (int g = 0; g < o.numGpus; ++g) joules += (double)(mj1[g] - mj0[g]) * 1e-3;
+        printf("ENERGY RESULTS\n");
+        printf("Energy (J) from writing samples to reading distortion (%dx), %.3f\n", o.nFrames, joules);
+        printf("Energy per frame (J), %.4f\n", joules / o.nFrames);
+        printf("Average power (W), %.1f\n", joules / ((t1 - t0 > 0 ? t1 - t0 : 1e-3) * 1e-3));
+    }
     print_timestamp("FINISHED HOST");
     return 0;
 }

@@ -3,6 +3,7 @@
 // overlap, FIFO collection.  Replaces the reference's OpenCL host plumbing (main.cpp:87-315,
 // 408-457, 560-598, 678-1250; main_aux_functions.h:585-630).  No CPU fallback exists.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -45,6 +46,8 @@ struct Slot {
     uint8_t* d_best_mode = nullptr;
     int32_t *h_cost = nullptr, *h_sad = nullptr, *h_satd = nullptr, *h_best_cost = nullptr;  // pinned
     uint8_t* h_best_mode = nullptr;
+    uint8_t *d_topk_mode = nullptr, *h_topk_mode = nullptr;   // top_k > 1 only
+    int32_t *d_topk_cost = nullptr, *h_topk_cost = nullptr;
     int64_t poc = 0;
     bool busy = false;
 };
@@ -84,13 +87,18 @@ static int check_cfg(const mipb200_config* c) {
     }
     if (c->slots < 1 || c->slots > 16) return fail(MIPB200_EINVAL, "slots %d out of range 1..16", c->slots);
     if (c->emit == 0 || (c->emit & ~7u)) return fail(MIPB200_EINVAL, "emit mask 0x%x invalid", c->emit);
+    if (c->top_k < 0 || c->top_k > MIPB200_TOPK_MAX) return fail(MIPB200_EINVAL, "top_k %d out of range 0..%d", c->top_k, MIPB200_TOPK_MAX);
+    if (c->bit_depth != 0 && c->bit_depth != 8 && c->bit_depth != 10 && c->bit_depth != 12)
+        return fail(MIPB200_EINVAL, "bit_depth %d not one of 0 (= 10), 8, 10, 12", c->bit_depth);
+    if (c->top_k > 1 && !(c->emit & MIPB200_EMIT_DECISIONS)) return fail(MIPB200_EINVAL, "top_k %d needs MIPB200_EMIT_DECISIONS", c->top_k);
     return MIPB200_OK;
 }
 
 static void free_slot(Slot& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFreeHost(s.h_frame); cudaFreeHost(s.h_cost); cudaFreeHost(s.h_sad); cudaFreeHost(s.h_satd);
-    cudaFreeHost(s.h_best_cost); cudaFreeHost(s.h_best_mode);
+    cudaFreeHost(s.h_best_cost); cudaFreeHost(s.h_best_mode); cudaFreeHost(s.h_topk_mode); cudaFreeHost(s.h_topk_cost);
+    cudaFree(s.d_topk_mode); cudaFree(s.d_topk_cost);
     cudaFree(s.d_frame); cudaFree(s.d_cost); cudaFree(s.d_sad); cudaFree(s.d_satd);
     cudaFree(s.d_best_cost); cudaFree(s.d_best_mode);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
@@ -131,17 +139,19 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
     }
     mipb200_engine* e = new mipb200_engine();
     e->cfg = *cfg;
+    if (e->cfg.bit_depth == 0) e->cfg.bit_depth = 10;
     e->n_ctus = mipb200_num_ctus(cfg->width, cfg->height);
     e->frame_bytes = (size_t)cfg->width * cfg->height * sizeof(uint16_t);
     e->cost_bytes = (size_t)e->n_ctus * MIP_COSTS_PER_CTU * sizeof(int32_t);
     e->cu_bytes4 = (size_t)e->n_ctus * MIP_CUS_PER_CTU * sizeof(int32_t);
     e->cu_bytes1 = (size_t)e->n_ctus * MIP_CUS_PER_CTU;
     e->slots.resize(cfg->slots);
-    if (mipb200::make_filter_params(cfg->filter_type, cfg->kernel_idx, &e->fp) != cudaSuccess) {
+    if (mipb200::make_filter_params(cfg->filter_type, cfg->kernel_idx, e->cfg.bit_depth, &e->fp) != cudaSuccess) {
         delete e;
         return fail(MIPB200_EINVAL, "filter parameters of filter_type %d kernel_idx %d failed their exactness check", cfg->filter_type, cfg->kernel_idx);
     }
     const bool wc = cfg->emit & MIPB200_EMIT_COSTS, ws = cfg->emit & MIPB200_EMIT_SAD_SATD, wd = cfg->emit & MIPB200_EMIT_DECISIONS;
+    const int tk = cfg->top_k > 1 ? cfg->top_k : 0;
 #define E_TRY(call)                                                                                     \
     do {                                                                                                \
         cudaError_t _e = (call);                                                                        \
@@ -160,9 +170,15 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
         E_TRY(cudaEventCreate(&s.ev_done));
         E_TRY(cudaHostAlloc((void**)&s.h_frame, e->frame_bytes, cudaHostAllocDefault));
         E_TRY(cudaMalloc((void**)&s.d_frame, e->frame_bytes));
-        if (wc) {   // decisions-only engines never materialise the 97840-entry table
+        if (wc || tk) {   // decisions-only engines never materialise the 97840-entry table; a top-k shortlist reads it
             E_TRY(cudaMalloc((void**)&s.d_cost, e->cost_bytes));
-            E_TRY(cudaHostAlloc((void**)&s.h_cost, e->cost_bytes, cudaHostAllocDefault));
+            if (wc) E_TRY(cudaHostAlloc((void**)&s.h_cost, e->cost_bytes, cudaHostAllocDefault));
+        }
+        if (tk) {
+            E_TRY(cudaMalloc((void**)&s.d_topk_mode, e->cu_bytes1 * tk));
+            E_TRY(cudaMalloc((void**)&s.d_topk_cost, e->cu_bytes4 * tk));
+            E_TRY(cudaHostAlloc((void**)&s.h_topk_mode, e->cu_bytes1 * tk, cudaHostAllocDefault));
+            E_TRY(cudaHostAlloc((void**)&s.h_topk_cost, e->cu_bytes4 * tk, cudaHostAllocDefault));
         }
         if (ws) {
             E_TRY(cudaMalloc((void**)&s.d_sad, e->cost_bytes));
@@ -194,7 +210,7 @@ MIPB200_API uint16_t* mipb200_next_input(mipb200_engine* e) {
 static int enqueue_kernels(mipb200_engine* e, const uint16_t* d_frame, int32_t* d_cost, int32_t* d_sad,
                            int32_t* d_satd, uint8_t* d_bm, int32_t* d_bc, cudaStream_t st) {
     const mipb200_config& c = e->cfg;
-    CU_TRY(mipb200::launch_costs(d_frame, c.width, c.height, e->fp, d_cost, d_sad, d_satd, d_bm, d_bc, st));
+    CU_TRY(mipb200::launch_costs(d_frame, c.width, c.height, c.bit_depth, e->fp, d_cost, d_sad, d_satd, d_bm, d_bc, st));
     e->launches++;
     return MIPB200_OK;
 }
@@ -218,7 +234,15 @@ MIPB200_API int mipb200_submit(mipb200_engine* e, const uint16_t* frame, int64_t
     CU_TRY(cudaEventRecord(s.ev_k0, s.stream));
     int rc = enqueue_kernels(e, s.d_frame, s.d_cost, s.d_sad, s.d_satd, s.d_best_mode, s.d_best_cost, s.stream);
     if (rc) return rc;
+    if (s.d_topk_mode) {
+        CU_TRY(mipb200::launch_topk(s.d_cost, e->n_ctus, e->cfg.top_k, s.d_topk_mode, s.d_topk_cost, s.stream));
+        e->launches++;
+    }
     CU_TRY(cudaEventRecord(s.ev_k1, s.stream));
+    if (s.h_topk_mode) {
+        CU_TRY(cudaMemcpyAsync(s.h_topk_mode, s.d_topk_mode, e->cu_bytes1 * e->cfg.top_k, cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(cudaMemcpyAsync(s.h_topk_cost, s.d_topk_cost, e->cu_bytes4 * e->cfg.top_k, cudaMemcpyDeviceToHost, s.stream));
+    }
     if (s.h_cost) CU_TRY(cudaMemcpyAsync(s.h_cost, s.d_cost, e->cost_bytes, cudaMemcpyDeviceToHost, s.stream));
     if (s.h_sad) {
         CU_TRY(cudaMemcpyAsync(s.h_sad, s.d_sad, e->cost_bytes, cudaMemcpyDeviceToHost, s.stream));
@@ -251,6 +275,9 @@ MIPB200_API int mipb200_collect(mipb200_engine* e, mipb200_result* out) {
     out->best_mode = s.h_best_mode;
     out->best_cost = s.h_best_cost;
     out->gpu_ms = ms;
+    out->top_k = s.h_topk_mode ? e->cfg.top_k : 0;
+    out->topk_mode = s.h_topk_mode;
+    out->topk_cost = s.h_topk_cost;
     s.busy = false;
     e->tail = (e->tail + 1) % (int)e->slots.size();
     e->in_flight--;
@@ -283,6 +310,61 @@ MIPB200_API int mipb200_decide_device(mipb200_engine* e, const int32_t* d_cost, 
     cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
     CU_TRY(mipb200::launch_decide(d_cost, e->n_ctus, d_best_mode, d_best_cost, st));
     e->launches++;
+    return MIPB200_OK;
+}
+
+MIPB200_API int mipb200_topk_device(mipb200_engine* e, const int32_t* d_cost, int k, uint8_t* d_modes, int32_t* d_costs, void* stream) {
+    if (!e || !d_cost || !d_modes || !d_costs) return fail(MIPB200_EINVAL, "NULL argument");
+    if (k < 1 || k > MIPB200_TOPK_MAX) return fail(MIPB200_EINVAL, "k %d out of range 1..%d", k, MIPB200_TOPK_MAX);
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
+    CU_TRY(mipb200::launch_topk(d_cost, e->n_ctus, k, d_modes, d_costs, st));
+    e->launches++;
+    return MIPB200_OK;
+}
+
+MIPB200_API int mipb200_pin_host(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return fail(MIPB200_EINVAL, "ptr and bytes are required");
+    CU_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return MIPB200_OK;
+}
+
+MIPB200_API int mipb200_unpin_host(void* ptr) {
+    if (!ptr) return fail(MIPB200_EINVAL, "ptr is NULL");
+    CU_TRY(cudaHostUnregister(ptr));
+    return MIPB200_OK;
+}
+
+// NVML through dlopen (libnvidia-ml.so.1 ships with the driver, not with the toolkit): the board's energy counter,
+// addressed by PCI bus id so that CUDA_VISIBLE_DEVICES reordering cannot pick the wrong board.
+MIPB200_API int mipb200_device_energy_mj(int device, unsigned long long* millijoules) {
+    typedef int (*init_fn)(void);
+    typedef int (*by_pci_fn)(const char*, void**);
+    typedef int (*energy_fn)(void*, unsigned long long*);
+    static std::mutex mu;
+    static void* lib = nullptr;
+    static by_pci_fn by_pci = nullptr;
+    static energy_fn energy = nullptr;
+    if (!millijoules) return fail(MIPB200_EINVAL, "millijoules is NULL");
+    std::lock_guard<std::mutex> lk(mu);
+    if (!lib) {
+        void* h = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!h) return fail(MIPB200_ENODEV, "NVML not available: %s", dlerror());
+        init_fn init = (init_fn)dlsym(h, "nvmlInit_v2");
+        by_pci = (by_pci_fn)dlsym(h, "nvmlDeviceGetHandleByPciBusId_v2");
+        energy = (energy_fn)dlsym(h, "nvmlDeviceGetTotalEnergyConsumption");
+        if (!init || !by_pci || !energy) { dlclose(h); return fail(MIPB200_ENODEV, "NVML lacks the energy-counter entry points"); }
+        const int rc = init();
+        if (rc != 0) { dlclose(h); return fail(MIPB200_ENODEV, "nvmlInit_v2 failed with %d", rc); }
+        lib = h;
+    }
+    char bus[32];
+    CU_TRY(cudaDeviceGetPCIBusId(bus, sizeof(bus), device));
+    void* dev = nullptr;
+    int rc = by_pci(bus, &dev);
+    if (rc != 0) return fail(MIPB200_ENODEV, "nvmlDeviceGetHandleByPciBusId(%s) failed with %d", bus, rc);
+    rc = energy(dev, millijoules);
+    if (rc != 0) return fail(MIPB200_ENODEV, "nvmlDeviceGetTotalEnergyConsumption failed with %d", rc);
     return MIPB200_OK;
 }
 

@@ -133,7 +133,8 @@ struct Ctx {
     const int* s_orig;        // [128][OS], holds orig + 1
     const uint16_t* s_refT;   // row slots:    sample (slot, x) at slot * RT_STRIDE + 8 + x
     const uint16_t* s_refL;   // column slots: sample (slot, y) at slot * RL_STRIDE + 8 + y
-    const uint16_t* s_dc;     // one cell holding 512
+    const uint16_t* s_dc;     // one cell holding 1 << (bitDepth - 1)
+    int maxv;                 // (1 << bitDepth) - 1
     uint32_t* s_red;          // this thread's column of the [RED_WORDS][NT] scratch
     const uint8_t* s_mat;
     int ctuX, tileY;          // frame position of the tile origin
@@ -176,8 +177,8 @@ __device__ __forceinline__ int diff_plain(int o1, int p) {   // (o + 1) - p - 1 
     asm("sub.s32 %0, %1, %2;" : "=r"(t) : "r"(o1), "r"(p));
     return t - 1;
 }
-// clamp to the 10-bit sample range in one VIMNMX.RELU: max(min(v, 1023), 0)   (intra.cl:482)
-__device__ __forceinline__ int clamp10(int v) { return __vimin_s32_relu(v, 1023); }
+// clamp to the sample range in one VIMNMX.RELU: max(min(v, maxv), 0), maxv = 1023 for the reference's 10 bits (intra.cl:482)
+__device__ __forceinline__ int clamp_px(int v, int maxv) { return __vimin_s32_relu(v, maxv); }
 
 // One 4x4 block given its 16 differences d = orig - pred (raster): SAD += sum|d| (one VABSDIFF
 // each), SATD += satd4x4(d).
@@ -277,7 +278,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
     int ipk[B];
     {
         int in[2 * B];
-        in[0] = (SID == 2) ? 0 : 512 - first;
+        in[0] = (SID == 2) ? 0 : ((c.maxv + 1) >> 1) - first;
 #pragma unroll
         for (int i = 1; i < 2 * B; ++i) in[i] = bd[i] - first;
 #pragma unroll
@@ -296,7 +297,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
                 int acc = 32;
                 acc = __dp2a_lo(ipk[0], cw, acc);
                 acc = __dp2a_hi(ipk[1], cw, acc);
-                p[a * 4 + b] = clamp10((acc >> 6) + first);
+                p[a * 4 + b] = clamp_px((acc >> 6) + first, c.maxv);
             }
         int d[16];
 #pragma unroll
@@ -324,7 +325,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
                     acc = __dp2a_hi(ipk[1], cw.x, acc);
                     acc = __dp2a_lo(ipk[2], cw.y, acc);
                     acc = __dp2a_hi(ipk[3], cw.y, acc);
-                    v[e] = clamp10((acc >> 6) + first);
+                    v[e] = clamp_px((acc >> 6) + first, c.maxv);
                 }
                 c.s_red[((a * R + b) >> 1) * NT] = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
             }
@@ -544,7 +545,7 @@ __device__ __forceinline__ void build_ref_tile(uint16_t* s_refT, uint16_t* s_ref
 // The fused kernel
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 2)
-mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams fp, int W, int H, int chunks,
+mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams fp, int W, int H, int chunks, int maxv,
                 int32_t* __restrict__ g_cost, int32_t* __restrict__ g_sad, int32_t* __restrict__ g_satd,
                 uint8_t* __restrict__ g_best_mode, int32_t* __restrict__ g_best_cost) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -606,7 +607,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     const int ordBeg = c_chunk_ord[half][chunk], ordCnt = c_chunk_ord[half][chunk + 1] - ordBeg;
     if (g_best_mode)
         for (int i = tid; i < ordCnt; i += NT) s_dec[i] = 0xffffffffu;
-    if (tid == 0) { *s_dc = 512; *s_next = 0; }
+    if (tid == 0) { *s_dc = (uint16_t)((maxv + 1) >> 1); *s_next = 0; }
     __syncthreads();                                      // tiles complete; the staging box may now be overwritten
 
     Ctx c;
@@ -614,6 +615,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     c.s_refT = s_refT;
     c.s_refL = s_refL;
     c.s_dc = s_dc;
+    c.maxv = maxv;
     c.s_red = s_red + tid;
     c.s_mat = s_mat;
     c.ctuX = ctuX;
@@ -793,6 +795,54 @@ mip_decide_kernel(const int32_t* __restrict__ cost, int n_ctus, uint8_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------
+// Top-k: the k cheapest modes of every CU in ascending (cost, mode) order, from a cost table.
+// One thread per CU; its 12/16/32 costs are one 16-byte aligned run (3/4/8 x LDG.128), kept in
+// registers as unique keys (cost << 6 | mode) and selected k times.  Skipped CUs -> 0xFF / -1.
+// ------------------------------------------------------------------------------------------
+template <int MODES>
+__device__ __forceinline__ void topk_cu(const int32_t* __restrict__ c, int k, uint8_t* __restrict__ om, int32_t* __restrict__ oc) {
+    uint32_t key[MODES];
+#pragma unroll
+    for (int q = 0; q < MODES / 4; ++q) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(c) + q);
+        key[4 * q] = ((uint32_t)v.x << 6) | (4 * q);
+        key[4 * q + 1] = ((uint32_t)v.y << 6) | (4 * q + 1);
+        key[4 * q + 2] = ((uint32_t)v.z << 6) | (4 * q + 2);
+        key[4 * q + 3] = ((uint32_t)v.w << 6) | (4 * q + 3);
+    }
+    const bool skipped = (key[0] >> 6) == 0x03ffffffu;   // cost -1
+    for (int j = 0; j < k; ++j) {
+        uint32_t best = 0xffffffffu;
+#pragma unroll
+        for (int m = 0; m < MODES; ++m) best = min(best, key[m]);
+#pragma unroll
+        for (int m = 0; m < MODES; ++m) key[m] = key[m] == best ? 0xffffffffu : key[m];
+        om[j] = skipped ? (uint8_t)0xFF : (uint8_t)(best & 63);
+        oc[j] = skipped ? -1 : (int32_t)(best >> 6);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mip_topk_kernel(const int32_t* __restrict__ cost, int n_ctus, int k, uint8_t* __restrict__ modes_out, int32_t* __restrict__ costs_out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_ctus * MIP_CUS_PER_CTU) return;
+    const int ctu = idx / MIP_CUS_PER_CTU, cu = idx - ctu * MIP_CUS_PER_CTU;
+    int lo = 0, hi = MIP_NUM_TYPES - 1;   // last type with cu_off <= cu
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)c_types[mid].cu_off <= cu) lo = mid; else hi = mid - 1;
+    }
+    const DevType& ty = c_types[lo];
+    const int modes = ty.modes;
+    const int32_t* c = cost + (size_t)ctu * MIP_COSTS_PER_CTU + ty.cost_off + (cu - ty.cu_off) * modes;
+    uint8_t* om = modes_out + (size_t)idx * k;
+    int32_t* oc = costs_out + (size_t)idx * k;
+    if (modes == 12) topk_cu<12>(c, k, om, oc);
+    else if (modes == 16) topk_cu<16>(c, k, om, oc);
+    else topk_cu<32>(c, k, om, oc);
+}
+
+// ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
 cudaError_t kernels_init(int chunks) {
@@ -938,7 +988,7 @@ static cudaError_t make_frame_map(const uint16_t* d_frame, int W, int H, CUtenso
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-cudaError_t make_filter_params(int ft, int kidx, FilterParams* fp) {
+cudaError_t make_filter_params(int ft, int kidx, int bit_depth, FilterParams* fp) {
     memset(fp, 0, sizeof(*fp));
     fp->type = ft;
     fp->kidx = kidx;
@@ -958,24 +1008,25 @@ cudaError_t make_filter_params(int ft, int kidx, FilterParams* fp) {
     if (is2d || is5) fp->full_den = sum2d;                         // 1-D 5x5 takes its interior denominator from the 2-D table
     else { const int k0 = mip_k3(kidx, -1, -1), k1 = mip_k3(kidx, -1, 0); fp->full_den = 4 * k0 + 4 * k1 + k1 * k1; }
     fp->full_magic = (uint32_t)((1ull << 32) / fp->full_den + 1);
-    // exactness of the multiply-high division over every numerator that can occur (weights x 1023 + den/2)
+    // exactness of the multiply-high division over every numerator that can occur (weights x max sample + den/2)
     int wsum = 0;
     for (int i = 0; i < N * N; ++i) wsum += fp->coef[i];
-    const uint64_t nmax = (uint64_t)wsum * 1023 + fp->full_den / 2;
+    const uint64_t nmax = (uint64_t)wsum * ((1u << bit_depth) - 1) + fp->full_den / 2;
     for (uint64_t n = 0; n <= nmax; ++n)
         if (((n * fp->full_magic) >> 32) != n / fp->full_den) return cudaErrorInvalidValue;
     return cudaSuccess;
 }
 
-cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, const FilterParams& fp, int32_t* d_cost, int32_t* d_sad,
+cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, int bit_depth, const FilterParams& fp, int32_t* d_cost, int32_t* d_sad,
                          int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, cudaStream_t st) {
+    if (bit_depth != 8 && bit_depth != 10 && bit_depth != 12) return cudaErrorInvalidValue;
     if ((d_best_mode == nullptr) != (d_best_cost == nullptr)) return cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(d_frame) & 15) != 0) return cudaErrorMisalignedAddress;   // TMA needs a 16-byte aligned frame
     CUtensorMap map;
     cudaError_t e = make_frame_map(d_frame, W, H, &map);
     if (e != cudaSuccess) return e;
     const int nctu = ((W + 127) >> 7) * ((H + 127) >> 7);
-    mip_cost_kernel<<<nctu * 2 * g_chunks, NT, SM_TOTAL, st>>>(map, fp, W, H, g_chunks, d_cost, d_sad, d_satd, d_best_mode, d_best_cost);
+    mip_cost_kernel<<<nctu * 2 * g_chunks, NT, SM_TOTAL, st>>>(map, fp, W, H, g_chunks, (1 << bit_depth) - 1, d_cost, d_sad, d_satd, d_best_mode, d_best_cost);
     return cudaGetLastError();
 }
 
@@ -992,6 +1043,14 @@ cudaError_t launch_filter(const uint16_t* d_in, uint16_t* d_out, int W, int H, i
 cudaError_t launch_decide(const int32_t* d_cost, int n_ctus, uint8_t* d_best_mode, int32_t* d_best_cost, cudaStream_t st) {
     const int n = n_ctus * MIP_CUS_PER_CTU;
     mip_decide_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_cost, n_ctus, d_best_mode, d_best_cost);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_topk(const int32_t* d_cost, int n_ctus, int k, uint8_t* d_modes, int32_t* d_costs, cudaStream_t st) {
+    if (k < 1 || k > MIP_TOPK_MAX) return cudaErrorInvalidValue;
+    if ((reinterpret_cast<uintptr_t>(d_cost) & 15) != 0) return cudaErrorMisalignedAddress;   // 128-bit loads of a CU's run
+    const int n = n_ctus * MIP_CUS_PER_CTU;
+    mip_topk_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_cost, n_ctus, k, d_modes, d_costs);
     return cudaGetLastError();
 }
 

@@ -19,7 +19,7 @@ struct FilterParams {
     int full_den;
     uint32_t full_magic;  // floor(n / full_den) == (n * full_magic) >> 32 for every numerator that can occur (checked)
 };
-cudaError_t make_filter_params(int filter_type, int kernel_idx, FilterParams* fp);
+cudaError_t make_filter_params(int filter_type, int kernel_idx, int bit_depth, FilterParams* fp);
 
 // Fused MIP kernel for one frame: TMA-staged tiles, optional low-pass filter of the reference samples
 // (filter_type 0 = original samples, 1..8 = availableFilters order) applied in shared memory, boundaries,
@@ -27,7 +27,8 @@ cudaError_t make_filter_params(int filter_type, int kernel_idx, FilterParams* fp
 // d_frame must be 16-byte aligned.
 // d_best_mode/d_best_cost (both or neither): per-CU argmin over the modes, produced by the same kernel.
 // d_cost may be null when only the decisions are wanted.
-cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, const FilterParams& fp, int32_t* d_cost,
+// bit_depth: 10 = the reference (clamp 1023, default sample 512: intra.cl:61, 446, 482); 8 and 12 scale those constants.
+cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, int bit_depth, const FilterParams& fp, int32_t* d_cost,
                          int32_t* d_sad, int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, cudaStream_t st);
 
 // Low-pass filter of a whole frame (alternative samples), filter_type 1..8.
@@ -37,5 +38,9 @@ cudaError_t launch_filter(const uint16_t* d_in, uint16_t* d_out, int W, int H, i
 // Per-CU argmin over the cost table.
 cudaError_t launch_decide(const int32_t* d_cost, int n_ctus, uint8_t* d_best_mode, int32_t* d_best_cost,
                           cudaStream_t st);
+
+// The k cheapest modes of every CU, ascending (cost, mode): modes [nCTU][5380][k] u8, costs [nCTU][5380][k] int32.
+#define MIP_TOPK_MAX 12   // the fewest modes any CU has (sizeId 2: 2 x 6 matrices)
+cudaError_t launch_topk(const int32_t* d_cost, int n_ctus, int k, uint8_t* d_modes, int32_t* d_costs, cudaStream_t st);
 
 }  // namespace mipb200

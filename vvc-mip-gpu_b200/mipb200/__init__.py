@@ -27,12 +27,13 @@ SKIPPED = -1
 EMIT_COSTS = 1
 EMIT_SAD_SATD = 2
 EMIT_DECISIONS = 4
+TOPK_MAX = 12
 
 # every symbol include/mipb200.h declares (tests/test_abi.py checks the header against this)
 ABI_SYMBOLS = (
     "mipb200_create", "mipb200_destroy", "mipb200_next_input", "mipb200_submit", "mipb200_collect",
     "mipb200_in_flight", "mipb200_num_ctus", "mipb200_run_device", "mipb200_filter_device",
-    "mipb200_decide_device", "mipb200_kernel_launches", "mipb200_sync", "mipb200_last_error",
+    "mipb200_decide_device", "mipb200_topk_device", "mipb200_kernel_launches", "mipb200_device_energy_mj", "mipb200_pin_host", "mipb200_unpin_host", "mipb200_sync", "mipb200_last_error",
     "mipb200_version",
 )
 
@@ -47,7 +48,7 @@ class Config(ctypes.Structure):
     _fields_ = [
         ("width", ctypes.c_int), ("height", ctypes.c_int), ("device", ctypes.c_int),
         ("filter_type", ctypes.c_int), ("kernel_idx", ctypes.c_int), ("slots", ctypes.c_int),
-        ("emit", ctypes.c_uint),
+        ("emit", ctypes.c_uint), ("top_k", ctypes.c_int), ("bit_depth", ctypes.c_int),
     ]
 
 
@@ -57,6 +58,7 @@ class Result(ctypes.Structure):
         ("cost", ctypes.POINTER(ctypes.c_int32)), ("sad", ctypes.POINTER(ctypes.c_int32)),
         ("satd", ctypes.POINTER(ctypes.c_int32)), ("best_mode", ctypes.POINTER(ctypes.c_uint8)),
         ("best_cost", ctypes.POINTER(ctypes.c_int32)), ("gpu_ms", ctypes.c_float),
+        ("top_k", ctypes.c_int), ("topk_mode", ctypes.POINTER(ctypes.c_uint8)), ("topk_cost", ctypes.POINTER(ctypes.c_int32)),
     ]
 
 
@@ -100,8 +102,16 @@ def lib() -> ctypes.CDLL:
         L.mipb200_filter_device.restype = ctypes.c_int
         L.mipb200_decide_device.argtypes = [vp, vp, vp, vp, vp]
         L.mipb200_decide_device.restype = ctypes.c_int
+        L.mipb200_topk_device.argtypes = [vp, vp, ctypes.c_int, vp, vp, vp]
+        L.mipb200_topk_device.restype = ctypes.c_int
         L.mipb200_kernel_launches.argtypes = [vp]
         L.mipb200_kernel_launches.restype = ctypes.c_longlong
+        L.mipb200_device_energy_mj.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
+        L.mipb200_device_energy_mj.restype = ctypes.c_int
+        L.mipb200_pin_host.argtypes = [vp, ctypes.c_size_t]
+        L.mipb200_pin_host.restype = ctypes.c_int
+        L.mipb200_unpin_host.argtypes = [vp]
+        L.mipb200_unpin_host.restype = ctypes.c_int
         L.mipb200_sync.argtypes = [vp]
         L.mipb200_sync.restype = ctypes.c_int
         L.mipb200_last_error.argtypes = []
@@ -115,6 +125,13 @@ def lib() -> ctypes.CDLL:
 def _check(rc: int) -> None:
     if rc != 0:
         raise MipError(rc, lib().mipb200_last_error().decode())
+
+
+def device_energy_mj(device: int = 0) -> int:
+    """Board energy counter in millijoules (NVML); raises MipError where NVML or the counter is missing."""
+    v = ctypes.c_ulonglong()
+    _check(lib().mipb200_device_energy_mj(device, ctypes.byref(v)))
+    return int(v.value)
 
 
 class FrameResult:
@@ -137,15 +154,18 @@ class FrameResult:
         self.satd = view(r.satd, (n, COSTS_PER_CTU), np.int32)
         self.best_mode = view(r.best_mode, (n, CUS_PER_CTU), np.uint8)
         self.best_cost = view(r.best_cost, (n, CUS_PER_CTU), np.int32)
+        self.top_k = int(r.top_k)
+        self.topk_mode = view(r.topk_mode, (n, CUS_PER_CTU, self.top_k), np.uint8) if self.top_k else None
+        self.topk_cost = view(r.topk_cost, (n, CUS_PER_CTU, self.top_k), np.int32) if self.top_k else None
 
 
 class Engine:
     """One GPU's MIP engine (mipb200_create .. mipb200_destroy)."""
 
     def __init__(self, width: int, height: int, device: int = 0, filter_type: int = 0, kernel_idx: int = 0,
-                 slots: int = 3, emit: int = EMIT_COSTS):
+                 slots: int = 3, emit: int = EMIT_COSTS, top_k: int = 0, bit_depth: int = 0):
         self._h = ctypes.c_void_p()
-        self.cfg = Config(width, height, device, filter_type, kernel_idx, slots, emit)
+        self.cfg = Config(width, height, device, filter_type, kernel_idx, slots, emit, top_k, bit_depth)
         _check(lib().mipb200_create(ctypes.byref(self._h), ctypes.byref(self.cfg)))
         self.width, self.height = width, height
         self.n_ctus = lib().mipb200_num_ctus(width, height)
@@ -203,6 +223,9 @@ class Engine:
 
     def decide_device(self, d_cost: int, d_best_mode: int, d_best_cost: int, stream: int = 0) -> None:
         _check(lib().mipb200_decide_device(self._h, d_cost, d_best_mode, d_best_cost, stream or None))
+
+    def topk_device(self, d_cost: int, k: int, d_modes: int, d_costs: int, stream: int = 0) -> None:
+        _check(lib().mipb200_topk_device(self._h, d_cost, k, d_modes, d_costs, stream or None))
 
     def kernel_launches(self) -> int:
         return int(lib().mipb200_kernel_launches(self._h))
