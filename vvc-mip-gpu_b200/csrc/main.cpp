@@ -380,15 +380,15 @@ void gpu_worker(Shared* sh, mipb200_engine* e, mipb200_config cfg, int g, int G)
         if (mipb200_collect(e, &r) != 0) { fprintf(stderr, "[!] ERROR (GPU %d): %s\n", cfg.device, mipb200_last_error()); sh->errors++; return false; }
         const int poc = (int)r.poc;
         if (wantLog && (poc == 0 || o.allFrames)) {   // the reference exports frame 0 only (main.cpp:1268)
-            sh->keepCost[poc].assign(r.cost, r.cost + ncost);
-            if (r.sad) { sh->keepSad[poc].assign(r.sad, r.sad + ncost); sh->keepSatd[poc].assign(r.satd, r.satd + ncost); }
+            memcpy(sh->keepCost[poc].data(), r.cost, ncost * sizeof(int32_t));
+            if (r.sad) { memcpy(sh->keepSad[poc].data(), r.sad, ncost * sizeof(int32_t)); memcpy(sh->keepSatd[poc].data(), r.satd, ncost * sizeof(int32_t)); }
         }
         if (wantDec) {
             const size_t ncu = (size_t)sh->nCtus * MIP_CUS_PER_CTU * (r.top_k ? r.top_k : 1);
             const uint8_t* bm = r.top_k ? r.topk_mode : r.best_mode;
             const int32_t* bc = r.top_k ? r.topk_cost : r.best_cost;
-            sh->keepMode[poc].assign(bm, bm + ncu);
-            sh->keepBest[poc].assign(bc, bc + ncu);
+            memcpy(sh->keepMode[poc].data(), bm, ncu);
+            memcpy(sh->keepBest[poc].data(), bc, ncu * sizeof(int32_t));
         }
         done += G;
         return true;
@@ -502,6 +502,17 @@ int main(int argc, char** argv) {
     }
     auto destroy_all = [&] { for (auto* e : engines) mipb200_destroy(e); };
     if (sh.errors) { destroy_all(); return 1; }
+    // host result arrays, allocated and touched here like the reference's return_* arrays (main.cpp:656-662)
+    {
+        const size_t ncost = (size_t)sh.nCtus * MIP_COSTS_PER_CTU, ncu = (size_t)sh.nCtus * MIP_CUS_PER_CTU * (o.topK > 1 ? o.topK : 1);
+        for (int poc = 0; poc < o.nFrames; ++poc) {
+            if (!o.noLog && (poc == 0 || o.allFrames)) {
+                sh.keepCost[poc].resize(ncost);
+                if (!o.compat) { sh.keepSad[poc].resize(ncost); sh.keepSatd[poc].resize(ncost); }
+            }
+            if (!o.decisionsLog.empty()) { sh.keepMode[poc].resize(ncu); sh.keepBest[poc].resize(ncu); }
+        }
+    }
     // page-lock the frames so that every upload is a DMA from where the samples already are (no staging copy)
     const bool pinned = mipb200_pin_host(frames.data(), frames.size() * sizeof(uint16_t)) == 0;
     print_timestamp("FINISH BUILD KERNELS");
