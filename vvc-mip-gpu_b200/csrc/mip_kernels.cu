@@ -142,16 +142,17 @@ struct Ctx {
 
 __device__ __forceinline__ int ilog2c(int v) { return v == 1 ? 0 : v == 2 ? 1 : v == 4 ? 2 : v == 8 ? 3 : v == 16 ? 4 : 5; }
 
-// 4x4 SATD of kernel_aux_functions.cl:142-249.  d = orig - pred in raster order.
+// 4x4 SATD of kernel_aux_functions.cl:142-249.  e = (orig - pred) + 1 in raster order: every difference carries the
+// same +1 (see diff_*() below), which reaches exactly one Hadamard coefficient, the DC one, as +16.
 // Three butterfly stages are explicit; the fourth is folded into the absolute sums:
 // |a + b| + |a - b| = |a - (-b)| + |a - b| = two VABSDIFF (abs-diff-accumulate) on (a, -b) and (a, b).
-// The DC pair is split because of the mean-scaled DC term (abs(d0) >> 2, :244-245).
-__device__ __forceinline__ int satd4x4(const int (&d)[16]) {
+// The DC pair is split because of the mean-scaled DC term (abs(d0) >> 2, :244-245); its -16 rides in the negation.
+__device__ __forceinline__ int satd4x4(const int (&e)[16]) {
     int m[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        int a0 = d[i] + d[12 + i], a1 = d[4 + i] + d[8 + i];
-        int a2 = d[4 + i] - d[8 + i], a3 = d[i] - d[12 + i];
+        int a0 = e[i] + e[12 + i], a1 = e[4 + i] + e[8 + i];
+        int a2 = e[4 + i] - e[8 + i], a3 = e[i] - e[12 + i];
         m[i] = a0 + a1; m[4 + i] = a2 + a3; m[8 + i] = a0 - a1; m[12 + i] = a3 - a2;
     }
     int s = 0, dc = 0;
@@ -159,7 +160,7 @@ __device__ __forceinline__ int satd4x4(const int (&d)[16]) {
     for (int r = 0; r < 4; ++r) {
         const int b0 = m[4 * r] + m[4 * r + 3], b1 = m[4 * r + 1] + m[4 * r + 2];
         const int b2 = m[4 * r + 1] - m[4 * r + 2], b3 = m[4 * r] - m[4 * r + 3];
-        if (r == 0) dc = __sad(b0, -b1, 0);          // |b0 + b1| = |coefficient 0|
+        if (r == 0) dc = __sad(b0, 16 - b1, 0);      // |b0 + b1 - 16| = |coefficient 0|
         else s = __sad(b0, -b1, s);
         s = __sad(b0, b1, s);
         s = __sad(b3, -b2, s);
@@ -168,24 +169,29 @@ __device__ __forceinline__ int satd4x4(const int (&d)[16]) {
     return (s + (dc >> 2) + 1) >> 1;
 }
 
-// The original-sample tile holds o + 1, so that the difference against an interpolated sample
-// floor(v / 2^s) costs one LEA.HI:  o - (v >> s) = (o + 1) + (~v >> s)   (two's complement).
-// A difference against a sample p that needs no shift is (o + 1) - p - 1.
+// Differences are kept as e = orig - pred + 1, one instruction each whatever the prediction looks like:
+//  * the original-sample tile holds o + 1, so against a sample p that needs no shift e = (o + 1) - p;
+//  * against an interpolated sample floor(v / 2^s):  o - (v >> s) = (o + 1) + (~v >> s)  (two's complement, one LEA.HI),
+//    and e = that + 1 = (o + 1) + ((~v + 2^s) >> s): the 2^s is folded into the start value of the running ~v.
+// The +1 is free downstream: SAD takes |e - 1| (VABSDIFF against 1), the SATD corrects its DC coefficient (above).
 __device__ __forceinline__ int diff_shifted(int o1, int nv, int s) { return o1 + (nv >> s); }
-__device__ __forceinline__ int diff_plain(int o1, int p) {   // (o + 1) - p - 1 as one IADD3 (the sub is opaque to LLVM,
-    int t;                                                   //  which would otherwise emit LOP3 ~p + IADD)
-    asm("sub.s32 %0, %1, %2;" : "=r"(t) : "r"(o1), "r"(p));
-    return t - 1;
+__device__ __forceinline__ int diff_plain(int o1, int p) { return o1 - p; }
+// -(a + b) as one IADD3 with both operands negated; opaque so that LLVM cannot rewrite (-(a + b)) >> 1 into a
+// shift plus a subtraction, which would cost the LEA.HI of diff_shifted().
+__device__ __forceinline__ int neg_sum(int a, int b) {
+    int t;
+    asm("{\n\t.reg .s32 u;\n\tadd.s32 u, %1, %2;\n\tneg.s32 %0, u;\n\t}" : "=r"(t) : "r"(a), "r"(b));
+    return t;
 }
 // clamp to the sample range in one VIMNMX.RELU: max(min(v, maxv), 0), maxv = 1023 for the reference's 10 bits (intra.cl:482)
 __device__ __forceinline__ int clamp_px(int v, int maxv) { return __vimin_s32_relu(v, maxv); }
 
-// One 4x4 block given its 16 differences d = orig - pred (raster): SAD += sum|d| (one VABSDIFF
-// each), SATD += satd4x4(d).
-__device__ __forceinline__ void block_cost_d(const int (&d)[16], int& sad, int& satd) {
+// One 4x4 block given its 16 offset differences e = orig - pred + 1 (raster): SAD += sum|e - 1| (one VABSDIFF
+// each), SATD += satd4x4(e).
+__device__ __forceinline__ void block_cost_d(const int (&e)[16], int& sad, int& satd) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) sad = __sad(d[k], 0, sad);
-    satd += satd4x4(d);
+    for (int k = 0; k < 16; ++k) sad = __sad(e[k], 1, sad);
+    satd += satd4x4(e);
 }
 
 __device__ __forceinline__ void load_o1_row(const int* o, int (&v)[4]) {
@@ -275,6 +281,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
     const bool tr = mode >= M;
     const int mat = tr ? mode - M : mode;
     const int first = bd[0];
+    const int acc0 = 32 + 64 * first;      // ((32 + sum) >> 6) + first == (32 + 64 * first + sum) >> 6   (intra.cl:454, 481)
     int ipk[B];
     {
         int in[2 * B];
@@ -294,10 +301,10 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const int cw = *reinterpret_cast<const int*>(mb + (a * 4 + b) * 4);
-                int acc = 32;
+                int acc = acc0;
                 acc = __dp2a_lo(ipk[0], cw, acc);
                 acc = __dp2a_hi(ipk[1], cw, acc);
-                p[a * 4 + b] = clamp_px((acc >> 6) + first, c.maxv);
+                p[a * 4 + b] = clamp_px(acc >> 6, c.maxv);
             }
         int d[16];
 #pragma unroll
@@ -320,12 +327,12 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int2 cw = *reinterpret_cast<const int2*>(mb + (a * R + b + e) * 8);
-                    int acc = 32;
+                    int acc = acc0;
                     acc = __dp2a_lo(ipk[0], cw.x, acc);
                     acc = __dp2a_hi(ipk[1], cw.x, acc);
                     acc = __dp2a_lo(ipk[2], cw.y, acc);
                     acc = __dp2a_hi(ipk[3], cw.y, acc);
-                    v[e] = clamp_px((acc >> 6) + first, c.maxv);
+                    v[e] = clamp_px(acc >> 6, c.maxv);
                 }
                 c.s_red[((a * R + b) >> 1) * NT] = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
             }
@@ -345,10 +352,10 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
                 for (int j = 0; j < R; ++j) {
                     int cur[4];
                     hor_row<R, UH>(c.s_red, j, s, (int)L[(j * UV + UV - 1) * stL], cur);
-                    // nv = ~(UV*prev + UV/2 + i*dl) walks down the rows; see diff_shifted()
+                    // nv = ~(UV*prev + UV/2 + i*dl) + UV walks down the rows; see diff_shifted()
                     int dl[4], nv[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { dl[k] = prev[k] - cur[k]; nv[k] = -UV * prev[k] - ((UV >> 1) + 1); }
+                    for (int k = 0; k < 4; ++k) { dl[k] = prev[k] - cur[k]; nv[k] = -UV * prev[k] + ((UV >> 1) - 1); }
 #pragma unroll
                     for (int blk = 0; blk < UV / 4; ++blk) {
                         int d[16];
@@ -376,13 +383,13 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
                     const int* o = orig + (4 * jp) * OS + x0;
                     load_o1_row(o, o1);            // row 0: (prev + c0 + 1) >> 1
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) d[k] = diff_shifted(o1[k], -prev[k] - c0[k] - 2, 1);
+                    for (int k = 0; k < 4; ++k) d[k] = diff_shifted(o1[k], neg_sum(prev[k], c0[k]), 1);     // ~(prev + c0 + 1) + 2
                     load_o1_row(o + OS, o1);       // row 1: c0
 #pragma unroll
                     for (int k = 0; k < 4; ++k) d[4 + k] = diff_plain(o1[k], c0[k]);
                     load_o1_row(o + 2 * OS, o1);   // row 2: (c0 + c1 + 1) >> 1
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) d[8 + k] = diff_shifted(o1[k], -c0[k] - c1[k] - 2, 1);
+                    for (int k = 0; k < 4; ++k) d[8 + k] = diff_shifted(o1[k], neg_sum(c0[k], c1[k]), 1);
                     load_o1_row(o + 3 * OS, o1);   // row 3: c1
 #pragma unroll
                     for (int k = 0; k < 4; ++k) { d[12 + k] = diff_plain(o1[k], c1[k]); prev[k] = c1[k]; }
@@ -622,8 +629,9 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     c.tileY = tileY;
 
     while (true) {
-        int wi = 0;
-        if (lane == 0) wi = atomicAdd(s_next, 1);
+        int wi;   // lane 0 draws the next warp task (a plain `if (lane == 0) atomicAdd` compiles to a 17-instruction vote/popc aggregation)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\tmov.s32 %0, 0;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
+                     : "=r"(wi) : "r"(lane), "r"(smem_u32(s_next)) : "memory");
         wi = __shfl_sync(0xffffffffu, wi, 0);
         if (wi >= wcnt) break;
         // warp task = 32 consecutive (CU, mode) pairs of one type: a warp touches at most 3-4 CUs, so the shared-memory
