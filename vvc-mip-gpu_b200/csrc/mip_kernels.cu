@@ -100,12 +100,12 @@ struct DevType {
 };
 
 __constant__ DevType c_types[MIP_NUM_TYPES];
-__constant__ uint32_t c_work[2][MAX_WORK];     // per half: type | (warp task index inside the type's half) << 8
 __constant__ int c_chunk_begin[2][MAX_CHUNKS + 1];
 // fused decisions: a chunk never splits the modes of a CU, so the CTA owns the argmin of its CUs
 constexpr int DEC_MAX = 2048;                  // CUs per chunk the shared-memory argmin table can hold
 __constant__ uint16_t c_chunk_ord[2][MAX_CHUNKS + 1];   // first CU ordinal of each chunk (per half)
 __constant__ uint16_t c_ord2cu[2][2700];       // CU ordinal inside a half -> CU index inside the CTU (0..5379)
+__device__ uint2 g_lane[2][MAX_WORK][32];      // per (half, warp task, lane): what the lane does, see the task loop of mip_cost_kernel
 __device__ uint8_t g_mat[MAT_BYTES];           // (coef - 32) as signed bytes, padded layout above
 
 static int g_chunks = 0;
@@ -237,6 +237,31 @@ __device__ __forceinline__ void hor_row(const uint32_t* s_red, int j, int s, int
     }
 }
 
+// Reduced boundary (intra.cl:127-141, 260-279): B rounded means over D consecutive 16-bit samples each, p 8-byte aligned
+// (CU positions are multiples of 4).  64-bit shared loads; IDP.2A against (1, 1) adds a pair of samples per instruction
+// and starts from the rounding offset D / 2.
+template <int B, int D>
+__device__ __forceinline__ void reduce_bdry(const uint16_t* p, int (&red)[B]) {
+    if constexpr (D == 1) {
+        const uint2 v = *reinterpret_cast<const uint2*>(p);
+        red[0] = v.x & 0xffff; red[1] = v.x >> 16; red[2] = v.y & 0xffff; red[3] = v.y >> 16;
+    } else {
+        uint32_t w[B * D / 2];
+#pragma unroll
+        for (int i = 0; i < B * D / 4; ++i) {
+            const uint2 v = reinterpret_cast<const uint2*>(p)[i];
+            w[2 * i] = v.x; w[2 * i + 1] = v.y;
+        }
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+            unsigned acc = D >> 1;
+#pragma unroll
+            for (int t = 0; t < D / 2; ++t) acc = __dp2a_lo(w[q * (D / 2) + t], 0x0101u, acc);
+            red[q] = (int)(acc >> ilog2c(D));
+        }
+    }
+}
+
 // One (CU, mode): everything from the boundaries to SAD/SATD.  SID = sizeId, W x H = CU size.
 // cuX, cuY are relative to the tile.  PARTS lanes share the (CU, mode): lane `part` takes a contiguous
 // 1/PARTS of the strips (every lane still computes the whole reduced prediction into its own scratch).
@@ -263,15 +288,17 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
     int bd[2 * B];
     {
         int redT[B], redL[B];
+        if (stT) reduce_bdry<B, DT>(T, redT);
+        else {   // frame edge: one replicated sample v, and (D * v + D / 2) >> log2(D) == v
+            const int v = T[0];
 #pragma unroll
-        for (int q = 0; q < B; ++q) {
-            int sT = 0, sL = 0;
+            for (int q = 0; q < B; ++q) redT[q] = v;
+        }
+        if (stL) reduce_bdry<B, DL>(L, redL);
+        else {
+            const int v = L[0];
 #pragma unroll
-            for (int t = 0; t < DT; ++t) sT += T[(q * DT + t) * stT];
-#pragma unroll
-            for (int t = 0; t < DL; ++t) sL += L[(q * DL + t) * stL];
-            redT[q] = (sT + (DT >> 1)) >> ilog2c(DT);
-            redL[q] = (sL + (DL >> 1)) >> ilog2c(DL);
+            for (int q = 0; q < B; ++q) redL[q] = v;
         }
         const bool tr = mode >= M;
 #pragma unroll
@@ -577,7 +604,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     const int ctuX = (ctu % ctuCols) << 7, tileY = ((ctu / ctuCols) << 7) + half * TILE_ROWS;
     const int rowsValid = min(TILE_ROWS, H - tileY);     // <= 0: the whole half lies below the frame
     const int wbeg = c_chunk_begin[half][chunk], wcnt = c_chunk_begin[half][chunk + 1] - wbeg;
-    const size_t ctuBase = (size_t)ctu * MIP_COSTS_PER_CTU;
+    const uint32_t ctuBase = (uint32_t)ctu * MIP_COSTS_PER_CTU;   // 32-bit element index: frames up to 43 000 CTUs
 
     if (rowsValid > 0) {
         // ---- stage: one TMA box (tile + halo) signalled on an mbarrier; the matrices come in meanwhile
@@ -628,26 +655,30 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     c.ctuX = ctuX;
     c.tileY = tileY;
 
-    while (true) {
-        int wi;   // lane 0 draws the next warp task (a plain `if (lane == 0) atomicAdd` compiles to a 17-instruction vote/popc aggregation)
+    // Warp tasks are drawn from a shared-memory counter, one ahead: the record of the next task (one coalesced 8-byte load
+    // from a table built once on the host -- the same 870 KB for every CTU, so it lives in L2) is requested before the
+    // current task's arithmetic starts, which hides the atomic + L2 latency of the draw behind ~1000 instructions of work.
+    // Record: .x = cuX | cuY << 7 | mode << 13 | strip group << 18 | inRange << 20 | CU type << 21, .y = cost index in
+    // the CTU | decision slot << 17.  0xffffffff in .x = no more work.
+    auto draw = [&]() -> uint2 {
+        int wi;   // lane 0 draws (a plain `if (lane == 0) atomicAdd` compiles to a 17-instruction vote/popc aggregation)
         asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\tmov.s32 %0, 0;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
                      : "=r"(wi) : "r"(lane), "r"(smem_u32(s_next)) : "memory");
         wi = __shfl_sync(0xffffffffu, wi, 0);
-        if (wi >= wcnt) break;
+        if (wi >= wcnt) return make_uint2(0xffffffffu, 0u);
+        return __ldg(&g_lane[half][wbeg + wi][lane]);
+    };
+    uint2 lr = draw();
+    while (lr.x != 0xffffffffu) {
+        const uint2 lr_next = draw();
         // warp task = 32 consecutive (CU, mode) pairs of one type: a warp touches at most 3-4 CUs, so the shared-memory
         // reads of originals and boundaries are mostly broadcasts (8 CUs x 4 modes per warp measured 60 % more bank conflicts)
-        const uint32_t rec = c_work[half][wbeg + wi];
-        const int t = rec & 0xff, wt = rec >> 8;
-        const DevType& ty = c_types[t];
-        const int modes = ty.modes, pl2 = ty.parts_log2;
-        const int ntask = (ty.n_cu[half] * modes) << pl2;
-        const int task = wt * 32 + lane;
-        const bool inRange = task < ntask;
-        const int tcl = inRange ? task : ntask - 1;
-        const int part = tcl & ((1 << pl2) - 1), cm = tcl >> pl2;
-        const int cuLocal = (int)(((uint32_t)cm * ty.mode_magic) >> 16), mode = cm - cuLocal * modes;
-        const int cu = ty.first_cu[half] + cuLocal;
-        const int cuX = ty.xs[cu & (ty.cols - 1)], cuY = ty.ys[cu >> ty.cols_log2] - half * TILE_ROWS;
+        const DevType& ty = c_types[(lr.x >> 21) & 63];
+        const int pl2 = ty.parts_log2;
+        const int cuX = lr.x & 127, cuY = (lr.x >> 7) & 63, mode = (lr.x >> 13) & 31, part = (lr.x >> 18) & 3;
+        const bool inRange = (lr.x >> 20) & 1;
+        const uint32_t coff = lr.y & 0x1ffffu;
+        const int slot = (int)(lr.y >> 17);
         const bool active = inRange && cuY + ty.h <= rowsValid && ctuX + cuX + ty.w <= W;   // CU fully inside the frame
         int sad = 0, satd = 0;
         if (__any_sync(0xffffffffu, active)) {
@@ -676,7 +707,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             }
         }
         if (inRange && part == 0) {
-            const size_t o = ctuBase + ty.cost_off + cu * modes + mode;
+            const uint32_t o = ctuBase + coff;
             const int cost = min(2 * sad, satd);            // intra.cl:1166
             if (g_cost) g_cost[o] = active ? cost : -1;
             if (g_sad) g_sad[o] = active ? sad : -1;
@@ -687,12 +718,13 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             // The lanes of one CU are first reduced in registers (MATCH.ANY + REDUX.MIN), then one lane per CU does the
             // shared-memory atomicMin: 3-4 distinct addresses per warp instead of 32 lanes serialising on them.
             const bool vote = inRange && part == 0 && active;
-            const unsigned grp = __match_any_sync(0xffffffffu, vote ? cuLocal : -1 - lane);
+            const unsigned grp = __match_any_sync(0xffffffffu, vote ? slot : -1 - lane);
             if (vote) {
                 const uint32_t best = __reduce_min_sync(grp, ((uint32_t)min(2 * sad, satd) << 6) | (uint32_t)mode);
-                if (lane == __ffs(grp) - 1) atomicMin(&s_dec[ty.cu_ord[half] + cuLocal - ordBeg], best);
+                if (lane == __ffs(grp) - 1) atomicMin(&s_dec[slot - ordBeg], best);
             }
         }
+        lr = lr_next;
     }
     if (g_best_mode) {
         __syncthreads();
@@ -861,6 +893,7 @@ cudaError_t kernels_init(int chunks) {
     DevType types[MIP_NUM_TYPES];
     memset(types, 0, sizeof(types));
     std::vector<uint32_t> work[2];
+    std::vector<uint2> lanes[2];          // 32 lane records per warp task
     std::vector<double> wcost[2];
     std::vector<char> cut_ok[2];          // may a chunk boundary follow this warp task? (no CU's modes may be split)
     std::vector<int> ord_after[2];        // CU ordinal reached after this warp task (valid where cut_ok)
@@ -897,6 +930,16 @@ cudaError_t kernels_init(int chunks) {
             const int nw = (ntask + 31) / 32;
             d.cu_ord[hf] = (uint16_t)ord_total[hf];
             for (int w = 0; w < nw; ++w) {
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int task = w * 32 + lane, in_range = task < ntask, tcl = in_range ? task : ntask - 1;
+                    const int part = tcl & ((1 << d.parts_log2) - 1), cm = tcl >> d.parts_log2;
+                    const int cu_local = cm / s.modes, mode = cm % s.modes, cu = d.first_cu[hf] + cu_local;
+                    const int cx = s.xs[cu % s.cols], cy = s.ys[cu / s.cols] - hf * TILE_ROWS;
+                    const uint32_t coff = s.cost_off + (uint32_t)cu * s.modes + mode, slot = (uint32_t)(ord_total[hf] + cu_local);
+                    if (cx > 127 || cy < 0 || cy > 63 || mode > 31 || part > 3 || coff >= (1u << 17) || slot >= (1u << 12)) return cudaErrorInvalidValue;
+                    lanes[hf].push_back(make_uint2((uint32_t)cx | ((uint32_t)cy << 7) | ((uint32_t)mode << 13) | ((uint32_t)part << 18) | ((uint32_t)in_range << 20) | ((uint32_t)t << 21),
+                                                   coff | (slot << 17)));
+                }
                 work[hf].push_back((uint32_t)t | ((uint32_t)w << 8));
                 wcost[hf].push_back(c);
                 const int done = std::min(ntask, 32 * (w + 1));
@@ -909,10 +952,8 @@ cudaError_t kernels_init(int chunks) {
         }
     }
     // contiguous, cost-balanced partition of each half's work list into `chunks` chunks
-    static uint32_t hwork[2][MAX_WORK];
     int begin[2][MAX_CHUNKS + 1];
     uint16_t chunk_ord[2][MAX_CHUNKS + 1];
-    memset(hwork, 0, sizeof(hwork));
     for (int hf = 0; hf < 2; ++hf) {
         if ((int)work[hf].size() > MAX_WORK) return cudaErrorInvalidValue;
         double total = 0;
@@ -928,10 +969,10 @@ cudaError_t kernels_init(int chunks) {
         while (k <= MAX_CHUNKS) { chunk_ord[hf][k] = (uint16_t)ord_total[hf]; begin[hf][k++] = (int)work[hf].size(); }
         for (int q = 0; q < chunks; ++q)
             if (chunk_ord[hf][q + 1] - chunk_ord[hf][q] > DEC_MAX) return cudaErrorInvalidValue;   // use more chunks
-        memcpy(hwork[hf], work[hf].data(), work[hf].size() * sizeof(uint32_t));
     }
     if ((err = cudaMemcpyToSymbol(c_types, types, sizeof(types))) != cudaSuccess) return err;
-    if ((err = cudaMemcpyToSymbol(c_work, hwork, sizeof(hwork))) != cudaSuccess) return err;
+    for (int hf = 0; hf < 2; ++hf)
+        if ((err = cudaMemcpyToSymbol(g_lane, lanes[hf].data(), lanes[hf].size() * sizeof(uint2), (size_t)hf * MAX_WORK * 32 * sizeof(uint2))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_chunk_begin, begin, sizeof(begin))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_chunk_ord, chunk_ord, sizeof(chunk_ord))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_ord2cu, ord2cu, sizeof(ord2cu))) != cudaSuccess) return err;
