@@ -199,40 +199,56 @@ __device__ __forceinline__ void load_o1_row(const int* o, int (&v)[4]) {
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
 
-// reduced-prediction sample (j, c) of this thread's scratch column (R samples per row)
-template <int R>
-__device__ __forceinline__ int red_at(const uint32_t* s_red, int j, int c) {
-    const int idx = j * R + c;
-    return reinterpret_cast<const uint16_t*>(s_red + (idx >> 1) * NT)[idx & 1];
+// The reduced prediction of a lane is a column of the [RED_WORDS][NT] scratch: sample (j, c) of an R-wide block is half
+// (c & 1) of word j * R / 2 + (c >> 1), words NT * 4 bytes apart.  The up-sampling loops walk it with byte pointers so
+// that every load has an immediate offset: StripPtr = where a strip's first reduced sample (and the one before it)
+// sits in row 0; a row is RED_ROWB<R> bytes further down.
+constexpr int RED_WB = NT * 4;                                     // bytes between consecutive words of a lane's column
+template <int R> constexpr int RED_ROWB = (R / 2) * RED_WB;        // bytes between reduced rows
+__device__ __forceinline__ int ld_u16(const char* p) { return *reinterpret_cast<const uint16_t*>(p); }
+
+struct StripPtr { const char *a, *b; bool first; int odd; };
+template <int UH>
+__device__ __forceinline__ StripPtr strip_ptr(const uint32_t* s_red, int s) {
+    const char* base = reinterpret_cast<const char*>(s_red);
+    StripPtr p;
+    if constexpr (UH == 1) { p.a = base + 2 * s * RED_WB; p.b = p.a; p.first = false; p.odd = 0; }          // c = 4s .. 4s+3
+    else if constexpr (UH == 2) { p.a = base + s * RED_WB; p.b = p.a - RED_WB + 2; p.first = s == 0; p.odd = 0; }   // c = 2s, 2s+1; before: 2s-1
+    else {
+        const int c = UH == 4 ? s : (s >> 1);                                                                   // one reduced column
+        p.a = base + (c >> 1) * RED_WB + (c & 1) * 2;
+        p.b = (c & 1) ? p.a - 2 : p.a - RED_WB + 2;
+        p.first = c == 0;
+        p.odd = s & 1;
+    }
+    return p;
 }
 
-// Horizontal up-sampling (A.4, intra.cl:818-844) of reduced row j for the four columns of
-// strip s (x0 = 4s).  Lval = refL[y] of that row (used only where x < UH).
+// Horizontal up-sampling (A.4, intra.cl:818-844) of one reduced row for the four columns of a strip.  pa / pb = the
+// strip's pointers moved to that row; Lval = refL[y] of the row (the sample before the first reduced column).
 __device__ __forceinline__ int avg_up(int a, int b) {   // (a + b + 1) >> 1 as IADD3 + SHF
     int t;
     asm("add.s32 %0, %1, %2;" : "=r"(t) : "r"(a), "r"(b));
     return (t + 1) >> 1;
 }
 
-template <int R, int UH>
-__device__ __forceinline__ void hor_row(const uint32_t* s_red, int j, int s, int Lval, int (&cur)[4]) {
+template <int UH>
+__device__ __forceinline__ void hor_row(const char* pa, const char* pb, bool first, int odd, int Lval, int (&cur)[4]) {
     if constexpr (UH == 1) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) cur[k] = red_at<R>(s_red, j, 4 * s + k);
+        cur[0] = ld_u16(pa); cur[1] = ld_u16(pa + 2); cur[2] = ld_u16(pa + RED_WB); cur[3] = ld_u16(pa + RED_WB + 2);
     } else if constexpr (UH == 2) {
-        const int a0 = red_at<R>(s_red, j, 2 * s), a1 = red_at<R>(s_red, j, 2 * s + 1);
-        const int bef = (s == 0) ? Lval : red_at<R>(s_red, j, 2 * s - 1);
+        const int a0 = ld_u16(pa), a1 = ld_u16(pa + 2);
+        const int bef = first ? Lval : ld_u16(pb);
         cur[0] = avg_up(bef, a0); cur[1] = a0; cur[2] = avg_up(a0, a1); cur[3] = a1;
     } else if constexpr (UH == 4) {
-        const int a = red_at<R>(s_red, j, s);
-        const int bef = (s == 0) ? Lval : red_at<R>(s_red, j, s - 1);
+        const int a = ld_u16(pa);
+        const int bef = first ? Lval : ld_u16(pb);
         const int dl = a - bef, v = 4 * bef + 2;
         cur[0] = (v + dl) >> 2; cur[1] = (v + 2 * dl) >> 2; cur[2] = (v + 3 * dl) >> 2; cur[3] = a;
     } else {  // UH == 8: two strips per reduced column
-        const int c = s >> 1;
-        const int a = red_at<R>(s_red, j, c);
-        const int bef = (c == 0) ? Lval : red_at<R>(s_red, j, c - 1);
-        const int dl = a - bef, v = 8 * bef + 4 + (s & 1) * 4 * dl;
+        const int a = ld_u16(pa);
+        const int bef = first ? Lval : ld_u16(pb);
+        const int dl = a - bef, v = 8 * bef + 4 + odd * 4 * dl;
         cur[0] = (v + dl) >> 3; cur[1] = (v + 2 * dl) >> 3; cur[2] = (v + 3 * dl) >> 3; cur[3] = (v + 4 * dl) >> 3;
     }
 }
@@ -370,6 +386,8 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 #pragma unroll 1
         for (int s = part * STRIPS; s < (part + 1) * STRIPS; ++s) {
             const int x0 = 4 * s;
+            const StripPtr sp = strip_ptr<UH>(c.s_red, s);
+            constexpr int ROWB = RED_ROWB<R>;
             int prev[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) prev[k] = T[(x0 + k) * stT];
@@ -378,7 +396,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 #pragma unroll 1
                 for (int j = 0; j < R; ++j) {
                     int cur[4];
-                    hor_row<R, UH>(c.s_red, j, s, (int)L[(j * UV + UV - 1) * stL], cur);
+                    hor_row<UH>(sp.a + j * ROWB, sp.b + j * ROWB, sp.first, sp.odd, (int)L[(j * UV + UV - 1) * stL], cur);
                     // nv = ~(UV*prev + UV/2 + i*dl) + UV walks down the rows; see diff_shifted()
                     int dl[4], nv[4];
 #pragma unroll
@@ -405,8 +423,8 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 #pragma unroll 1
                 for (int jp = 0; jp < R / 2; ++jp) {
                     int c0[4], c1[4], d[16], o1[4];
-                    hor_row<R, UH>(c.s_red, 2 * jp, s, (int)L[(4 * jp + 1) * stL], c0);
-                    hor_row<R, UH>(c.s_red, 2 * jp + 1, s, (int)L[(4 * jp + 3) * stL], c1);
+                    hor_row<UH>(sp.a + 2 * jp * ROWB, sp.b + 2 * jp * ROWB, sp.first, sp.odd, (int)L[(4 * jp + 1) * stL], c0);
+                    hor_row<UH>(sp.a + (2 * jp + 1) * ROWB, sp.b + (2 * jp + 1) * ROWB, sp.first, sp.odd, (int)L[(4 * jp + 3) * stL], c1);
                     const int* o = orig + (4 * jp) * OS + x0;
                     load_o1_row(o, o1);            // row 0: (prev + c0 + 1) >> 1
 #pragma unroll
@@ -429,7 +447,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         int cur[4], o1[4];
-                        hor_row<R, UH>(c.s_red, 4 * jq + i, s, (int)L[(4 * jq + i) * stL], cur);
+                        hor_row<UH>(sp.a + (4 * jq + i) * ROWB, sp.b + (4 * jq + i) * ROWB, sp.first, sp.odd, (int)L[(4 * jq + i) * stL], cur);
                         load_o1_row(orig + (4 * jq + i) * OS + x0, o1);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) d[4 * i + k] = diff_plain(o1[k], cur[k]);
@@ -660,17 +678,20 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     // current task's arithmetic starts, which hides the atomic + L2 latency of the draw behind ~1000 instructions of work.
     // Record: .x = cuX | cuY << 7 | mode << 13 | strip group << 18 | inRange << 20 | CU type << 21, .y = cost index in
     // the CTU | decision slot << 17.  0xffffffff in .x = no more work.
-    auto draw = [&]() -> uint2 {
-        int wi;   // lane 0 draws (a plain `if (lane == 0) atomicAdd` compiles to a 17-instruction vote/popc aggregation)
+    auto draw = [&](uint32_t zero) -> uint2 {
+        // Lane 0 draws.  ptxas wraps an atomic on a warp-uniform address into a vote / popc / shuffle aggregation (17
+        // instructions); `zero` -- bits of a loaded record that are always 0, which the compiler cannot know -- makes the
+        // address formally per-lane and leaves a single predicated ATOMS.ADD.
+        int wi;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\tmov.s32 %0, 0;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
-                     : "=r"(wi) : "r"(lane), "r"(smem_u32(s_next)) : "memory");
+                     : "=r"(wi) : "r"(lane), "r"(smem_u32(s_next) + zero) : "memory");
         wi = __shfl_sync(0xffffffffu, wi, 0);
         if (wi >= wcnt) return make_uint2(0xffffffffu, 0u);
         return __ldg(&g_lane[half][wbeg + wi][lane]);
     };
-    uint2 lr = draw();
+    uint2 lr = draw((__ldg(&g_lane[half][wbeg][lane]).y >> 30) << 2);
     while (lr.x != 0xffffffffu) {
-        const uint2 lr_next = draw();
+        const uint2 lr_next = draw((lr.y >> 30) << 2);
         // warp task = 32 consecutive (CU, mode) pairs of one type: a warp touches at most 3-4 CUs, so the shared-memory
         // reads of originals and boundaries are mostly broadcasts (8 CUs x 4 modes per warp measured 60 % more bank conflicts)
         const DevType& ty = c_types[(lr.x >> 21) & 63];
