@@ -60,12 +60,15 @@ constexpr int RED_WORDS = 32;           // packed reduced-prediction words per t
 // different matrices at the same row: the per-matrix pads spread the matrices over distinct banks, and each permuted
 // copy starts a whole number of bank groups after the plain one (48 B / 64 B / 64 B modulo 128), so plain and transposed
 // lanes never collide either.
-constexpr int M2_STRIDE = 520, M1_STRIDE = 136, M0_STRIDE = 68;   // 64x8 B + 8, 16x8 B + 8, 16x4 B + 4
-constexpr int M2_OFF = 0, M2T_OFF = M2_OFF + 6 * M2_STRIDE;       // 3120 = 24*128 + 48
-constexpr int M1_OFF = M2T_OFF + 6 * M2_STRIDE, M1T_OFF = M1_OFF + 8 * M1_STRIDE;    // +1088 = 8*128 + 64
-constexpr int M0_OFF = M1T_OFF + 8 * M1_STRIDE, M0T_OFF = M0_OFF + 16 * M0_STRIDE;   // +1088
-constexpr int MAT_BYTES = M0T_OFF + 16 * M0_STRIDE;   // 10592
-static_assert((M2T_OFF - M2_OFF) % 128 == 48 && (M1T_OFF - M1_OFF) % 128 == 64 && (M0T_OFF - M0_OFF) % 128 == 64, "bank phases");
+constexpr int M2_STRIDE = 528, M1_STRIDE = 144, M0_STRIDE = 68;   // 64x8 B + 16, 16x8 B + 16, 16x4 B + 4
+constexpr int M2_OFF = 0, M2T_OFF = M2_OFF + 6 * M2_STRIDE;       // 3168 = 24*128 + 96
+constexpr int M1_OFF = M2T_OFF + 6 * M2_STRIDE, M1T_OFF = M1_OFF + 8 * M1_STRIDE;    // +1152 = 9*128
+constexpr int M0_OFF = M1T_OFF + 8 * M1_STRIDE, M0T_OFF = M0_OFF + 16 * M0_STRIDE;   // +1088 = 8*128 + 64
+constexpr int MAT_BYTES = M0T_OFF + 16 * M0_STRIDE;   // 10816
+// sizeId 2 / 1: two 8-byte rows per LDS.128, so matrices start 16-byte aligned and 4 banks apart (6 + 6 or 8 + 8 matrices
+// of a warp = 12 or 16 distinct 16-byte rows = the minimum of 2 wavefronts); sizeId 0: 4-byte rows, 1 bank apart.
+static_assert(M2_STRIDE % 16 == 0 && M1_STRIDE % 16 == 0 && M2T_OFF % 16 == 0 && M1_OFF % 16 == 0 && M1T_OFF % 16 == 0, "LDS.128 alignment");
+static_assert((M2_STRIDE / 4) % 32 == 4 && (M1_STRIDE / 4) % 32 == 4 && (M0T_OFF - M0_OFF) % 128 == 64, "bank phases");
 
 constexpr int SM_RED = 0;                                      // first: the TMA box lands here (128-byte aligned)
 constexpr int SM_RED_BYTES = RED_WORDS * NT * 4;               // 49152 at NT = 384
@@ -362,23 +365,23 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
     } else {
         // ---- A.3 matrix-vector product -> private scratch column, two samples per word
         const uint8_t* mb = c.s_mat + (SID == 2 ? (tr ? M2T_OFF : M2_OFF) + mat * M2_STRIDE : (tr ? M1T_OFF : M1_OFF) + mat * M1_STRIDE);
+        const char* mp = reinterpret_cast<const char*>(mb);     // matrix rows a*R + b (8 taps each), two per 16-byte load
+        char* wp = reinterpret_cast<char*>(c.s_red);            // words of this lane's scratch column, RED_WB bytes apart
 #pragma unroll 1
         for (int a = 0; a < R; ++a) {
 #pragma unroll
             for (int b = 0; b < R; b += 2) {
-                int v[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int2 cw = *reinterpret_cast<const int2*>(mb + (a * R + b + e) * 8);
-                    int acc = acc0;
-                    acc = __dp2a_lo(ipk[0], cw.x, acc);
-                    acc = __dp2a_hi(ipk[1], cw.x, acc);
-                    acc = __dp2a_lo(ipk[2], cw.y, acc);
-                    acc = __dp2a_hi(ipk[3], cw.y, acc);
-                    v[e] = clamp_px(acc >> 6, c.maxv);
-                }
-                c.s_red[((a * R + b) >> 1) * NT] = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
+                const int4 cw = *reinterpret_cast<const int4*>(mp + b * 8);
+                int acc = acc0, acd = acc0;
+                acc = __dp2a_lo(ipk[0], cw.x, acc);  acd = __dp2a_lo(ipk[0], cw.z, acd);
+                acc = __dp2a_hi(ipk[1], cw.x, acc);  acd = __dp2a_hi(ipk[1], cw.z, acd);
+                acc = __dp2a_lo(ipk[2], cw.y, acc);  acd = __dp2a_lo(ipk[2], cw.w, acd);
+                acc = __dp2a_hi(ipk[3], cw.y, acc);  acd = __dp2a_hi(ipk[3], cw.w, acd);
+                const uint32_t v0 = (uint32_t)clamp_px(acc >> 6, c.maxv), v1 = (uint32_t)clamp_px(acd >> 6, c.maxv);
+                *reinterpret_cast<uint32_t*>(wp + (b >> 1) * RED_WB) = __byte_perm(v0, v1, 0x5410);   // v0 | v1 << 16
             }
+            mp += R * 8;
+            wp += RED_ROWB<R>;
         }
         // ---- A.4 + A.5 strip-wise: 4 columns at a time, top to bottom
         const int* orig = c.s_orig + cuY * OS + cuX;
