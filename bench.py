@@ -359,9 +359,14 @@ def main():
                          "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms_per_frame": kernel_ms,
                          "note": "path is INT32-issue bound (BASELINE.md section 2); see int32"},
+            # frac: the kernel alone, launches back to back on one stream (each launch pays its own ramp-up and tail);
+            # frac_timed_region: the same launches inside the timed region, where frames overlap on the slot streams
+            # (timed-region time / launches: what one launch costs the GPU in steady state)
             "int32": {"achieved_tops": OPS_PER_FRAME / (kernel_ms * 1e-3) / 1e12, "peak_tops": int32_peak,
                       "frac": OPS_PER_FRAME / (kernel_ms * 1e-3) / 1e12 / int32_peak, "peak_source": int32_src,
-                      "ops_per_frame": OPS_PER_FRAME},
+                      "ops_per_frame": OPS_PER_FRAME,
+                      "ms_per_launch_timed_region": dev_ms / max(1, launches),
+                      "frac_timed_region": OPS_PER_FRAME * value / world / 1e12 / int32_peak},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
