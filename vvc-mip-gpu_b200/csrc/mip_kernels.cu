@@ -45,7 +45,6 @@ namespace mipb200 {
 #define MIP_NT 384
 #endif
 constexpr int NT = MIP_NT;              // threads per CTA
-constexpr int NWARPS = NT / 32;
 constexpr int OS = 132;                 // s_orig row stride in int32 words (128 + 4: rows shift 4 banks)
 // Reference samples are only ever read on the row above / the column left of a CU, and every CU origin is a multiple
 // of 4: the reference tile keeps 18 row slots (halo row -1, rows 3,7,..,63, frame row 0) and 34 column slots (halo
