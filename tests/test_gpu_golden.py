@@ -51,3 +51,23 @@ def test_filters_equal_reference_opencl(mip, path):
             assert np.array_equal(got, z[f"f{ft}k{kidx}"]), f"filter_type={ft} kernel_idx={kidx}"
             n += 1
     assert n == 32
+
+
+def _fullsize():
+    import test_oracle_golden as G
+    return G
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", __import__("test_oracle_golden")._fullsize_cases(),
+                         ids=lambda c: f"{c['width']}x{c['height']}_f{c['filter_type']}k{c['kernel_idx']}")
+def test_engine_equals_reference_opencl_on_whole_frames(mip, case):
+    """The CUDA engine against the reference's own OpenCL output for whole 1080p / 2160p frames (per-CTU hashes), no oracle
+    in between."""
+    G = _fullsize()
+    m = G.fullsize_helpers()
+    f = G.fullsize_frame(case)
+    with mip.Engine(case["width"], case["height"], filter_type=case["filter_type"], kernel_idx=case["kernel_idx"], slots=1) as eng:
+        got = m.ctu_hashes(eng.run(f).cost, case["width"], case["height"])
+    bad = [i for i, (a, b) in enumerate(zip(got, case["sha256_16_per_ctu"])) if a != b]
+    assert len(got) == len(case["sha256_16_per_ctu"]) and not bad, f"CTUs that differ from the reference: {bad[:20]}"

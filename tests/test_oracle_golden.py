@@ -116,3 +116,35 @@ def test_oracle_filters_equal_reference_opencl_kernels_on_b200(oracle, path):
             assert np.array_equal(got, want), f"filter_type={ft} kernel_idx={kidx}: {int((got != want).sum())} pixels differ"
             n += 1
     assert n == 32
+
+
+# ---- whole BASELINE-size frames: per-CTU hashes of the reference's OpenCL output on a B200 (make_ocl_fullsize_hashes.py)
+def _fullsize_cases():
+    p = os.path.join(GOLD, "ocl_b200_fullsize_hashes.json")
+    return json.load(open(p)) if os.path.exists(p) else []
+
+
+def fullsize_helpers():
+    import importlib.util
+    import sys
+    sys.path.insert(0, GOLD)
+    spec = importlib.util.spec_from_file_location("make_ocl_fullsize_hashes", os.path.join(GOLD, "make_ocl_fullsize_hashes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def fullsize_frame(case):
+    w, h, seed = case["width"], case["height"], case["seed"]
+    return frames.noise_frame(w, h, seed) if case["frame_kind"] == "noise" else frames.natural_frame(w, h, seed)
+
+
+@pytest.mark.parametrize("case", _fullsize_cases(), ids=lambda c: f"{c['width']}x{c['height']}_f{c['filter_type']}k{c['kernel_idx']}")
+def test_oracle_equals_reference_opencl_on_whole_frames(oracle, case):
+    """1080p (original samples, the bench configuration, a 3x3 filter) and 2160p: every CTU of the oracle's table hashes to
+    what the reference's unmodified kernels produced on the B200 (CUs not fully inside the frame masked to -1)."""
+    m = fullsize_helpers()
+    cost = oracle.run_frame(fullsize_frame(case), case["filter_type"], case["kernel_idx"])
+    got = m.ctu_hashes(cost, case["width"], case["height"])
+    bad = [i for i, (a, b) in enumerate(zip(got, case["sha256_16_per_ctu"])) if a != b]
+    assert len(got) == len(case["sha256_16_per_ctu"]) and not bad, f"CTUs that differ from the reference: {bad[:20]}"
