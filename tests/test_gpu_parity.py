@@ -262,3 +262,31 @@ def test_widths_that_are_not_multiples_of_128(mip, oracle, shape, ft, kidx):
     bm, bc = oracle.decisions(want)
     _assert_same(got["best_mode"], bm, "best_mode")
     assert np.array_equal(got["best_mode"] != 0xFF, T.in_frame_mask(w, h))
+
+
+def test_random_geometries(mip, oracle):
+    """Seeded sweep over odd-but-legal geometries (W % 8 == 0, H % 4 == 0: partial right and bottom CTUs, single partial
+    CTU, one-row-of-4 frames), contents, filters and bit depths; cost, SAD, SATD and decisions against the oracle."""
+    from mipb200 import frames, tables as T
+    rng = np.random.default_rng(20261018)
+    for it in range(14):
+        w = int(rng.integers(1, 61)) * 8
+        h = int(rng.integers(1, 81)) * 4
+        ft = int(rng.integers(0, 9))
+        kidx = int(rng.integers(0, T.num_kernel_idx(ft))) if ft else 0
+        bits = (10, 10, 8, 12)[it % 4]
+        kind = it % 3
+        f = (frames.noise_frame(w, h, 100 + it, bits=bits) if kind == 0 else
+             frames.natural_frame(w, h, 100 + it, bits=bits) if kind == 1 else
+             (rng.integers(0, 2, size=(h, w)) * ((1 << bits) - 1)).astype(np.uint16))
+        want = oracle.run_frame(f, ft, kidx, want_sad_satd=True, bit_depth=bits)
+        with mip.Engine(w, h, filter_type=ft, kernel_idx=kidx, slots=1, bit_depth=bits,
+                        emit=mip.EMIT_COSTS | mip.EMIT_SAD_SATD | mip.EMIT_DECISIONS) as eng:
+            r = eng.run(f)
+            tag = f"{w}x{h} ft={ft} k={kidx} bits={bits} kind={kind}"
+            _assert_same(r.cost, want[0], tag + " cost")
+            _assert_same(r.sad, want[1], tag + " sad")
+            _assert_same(r.satd, want[2], tag + " satd")
+            bm, bc = oracle.decisions(want[0])
+            _assert_same(r.best_mode, bm, tag + " best_mode")
+            _assert_same(r.best_cost, bc, tag + " best_cost")
