@@ -16,7 +16,9 @@
 //   lane = one (CU, mode) pair = one output cost.  32 consecutive (CU, mode) pairs of one CU
 //          type form a warp task, so all lanes run the same shape-specialised code, nothing
 //          is reduced across lanes, there is no barrier after staging, and the 32 costs of a
-//          warp leave as one coalesced 128-byte store in the reference's buffer order.
+//          warp leave as one coalesced 128-byte store in the reference's buffer order.  Tasks are
+//          drawn from a shared-memory counter one ahead; what each lane does in a task is a
+//          ready-made 8-byte record of an L2-resident table (g_lane) built once on the host.
 //   per lane: reduced boundaries (A.2) -> matrix-vector product with IDP.2A on (coef-32)
 //          signed bytes (A.3) into a private shared-memory column -> strip-wise bilinear
 //          up-sampling (A.4) -> per 4x4 block: difference, SAD, Hadamard SATD (A.5).
@@ -90,15 +92,10 @@ static_assert(SM_RED % 128 == 0, "TMA destination must be 128-byte aligned");
 constexpr int MAX_CHUNKS = 64;
 constexpr int MAX_WORK = 1700;          // warp tasks per CTU half
 
-struct DevType {
-    uint8_t w, h, cols, rows, size_id, modes, shape, cols_log2;
-    uint16_t n, nwt;       // CUs per CTU, warp tasks per CTU
-    uint32_t mode_magic;   // task / modes == (task * mode_magic) >> 16 for every task of the type
-    uint16_t first_cu[2], n_cu[2];   // CUs of the type that lie in the top / bottom half of the CTU (contiguous in CU order)
+struct DevType {               // what device code needs to know about a CU type; everything positional is in g_lane
+    uint8_t w, h, modes, shape;
     uint8_t parts_log2, pad[3];      // lanes that share one (CU, mode): 4 for 64x64 (a quarter of the strips each), else 1
-    uint16_t cu_ord[2];              // ordinal of the type's first CU among all CUs of the top / bottom half
-    uint32_t cost_off, cu_off;
-    uint8_t xs[32], ys[32];
+    uint32_t cost_off, cu_off;       // first cost / first CU of the type inside a CTU
 };
 
 __constant__ DevType c_types[MIP_NUM_TYPES];
@@ -925,17 +922,9 @@ cudaError_t kernels_init(int chunks) {
     for (int t = 0; t < MIP_NUM_TYPES; ++t) {
         const mip_cu_type_t& s = MIP_TYPES[t];
         DevType& d = types[t];
-        d.w = s.w; d.h = s.h; d.cols = s.cols; d.rows = s.rows; d.size_id = s.size_id; d.modes = s.modes;
+        d.w = s.w; d.h = s.h; d.modes = s.modes;
         d.shape = (uint8_t)shape_of(s.w, s.h);
-        d.n = s.n; d.nwt = (uint16_t)((s.n * s.modes + 31) / 32);
-        d.cols_log2 = 0;
-        while ((1 << d.cols_log2) < s.cols) d.cols_log2++;
-        if ((1 << d.cols_log2) != s.cols) return cudaErrorInvalidValue;   // every CU grid has a power-of-two column count
-        d.mode_magic = (65536u + s.modes - 1) / s.modes;
-        for (int task = 0; task < s.n * s.modes; ++task)
-            if ((int)(((uint32_t)task * d.mode_magic) >> 16) != task / s.modes) return cudaErrorInvalidValue;
         d.cost_off = s.cost_off; d.cu_off = s.cu_off;
-        memcpy(d.xs, s.xs, 32); memcpy(d.ys, s.ys, 32);
         d.parts_log2 = (s.w == 64 && s.h == 64) ? 2 : 0;
         // CUs per CTU half: CU order is raster, so each half is one contiguous run; no CU crosses y = 64
         for (int hf = 0; hf < 2; ++hf) {
@@ -945,18 +934,16 @@ cudaError_t kernels_init(int chunks) {
                 if (y / 64 != (y + s.h - 1) / 64) return cudaErrorInvalidValue;
                 if (y / 64 == hf) { if (first < 0) first = cu; else if (cu != first + cnt) return cudaErrorInvalidValue; cnt++; }
             }
-            d.first_cu[hf] = (uint16_t)(first < 0 ? 0 : first);
-            d.n_cu[hf] = (uint16_t)cnt;
+            const int first_cu = first < 0 ? 0 : first;
             const double mv = s.size_id == 2 ? 700.0 : (s.size_id == 1 ? 200.0 : 120.0);
             const double c = (mv + 11.0 * s.w * s.h + 2.0 * (s.w + s.h) + 60.0) / (1 << d.parts_log2) + (d.parts_log2 ? mv : 0.0);
             const int per_cu = s.modes << d.parts_log2, ntask = cnt * per_cu;
             const int nw = (ntask + 31) / 32;
-            d.cu_ord[hf] = (uint16_t)ord_total[hf];
             for (int w = 0; w < nw; ++w) {
                 for (int lane = 0; lane < 32; ++lane) {
                     const int task = w * 32 + lane, in_range = task < ntask, tcl = in_range ? task : ntask - 1;
                     const int part = tcl & ((1 << d.parts_log2) - 1), cm = tcl >> d.parts_log2;
-                    const int cu_local = cm / s.modes, mode = cm % s.modes, cu = d.first_cu[hf] + cu_local;
+                    const int cu_local = cm / s.modes, mode = cm % s.modes, cu = first_cu + cu_local;
                     const int cx = s.xs[cu % s.cols], cy = s.ys[cu / s.cols] - hf * TILE_ROWS;
                     const uint32_t coff = s.cost_off + (uint32_t)cu * s.modes + mode, slot = (uint32_t)(ord_total[hf] + cu_local);
                     if (cx > 127 || cy < 0 || cy > 63 || mode > 31 || part > 3 || coff >= (1u << 17) || slot >= (1u << 12)) return cudaErrorInvalidValue;
@@ -969,7 +956,7 @@ cudaError_t kernels_init(int chunks) {
                 cut_ok[hf].push_back(done % per_cu == 0);
                 ord_after[hf].push_back(ord_total[hf] + done / per_cu);
             }
-            for (int k = 0; k < cnt; ++k) ord2cu[hf][ord_total[hf] + k] = (uint16_t)(s.cu_off + d.first_cu[hf] + k);
+            for (int k = 0; k < cnt; ++k) ord2cu[hf][ord_total[hf] + k] = (uint16_t)(s.cu_off + first_cu + k);
             ord_total[hf] += cnt;
             if (ord_total[hf] > 2700) return cudaErrorInvalidValue;
         }
