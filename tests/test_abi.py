@@ -67,3 +67,21 @@ def test_product_never_touches_the_oracle():
                     if re.search(r"oracle[/.]|import oracle|mip_oracle|libmip_oracle", txt):
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_create_validates_the_configuration_before_touching_cuda(mip):
+    """Bad geometry / filter / shortlist / depth are MIPB200_EINVAL (-1) with a message, also on a box without a GPU; a
+    valid configuration on such a box is MIPB200_ENODEV (-3): there is no CPU fallback."""
+    import pytest
+    for kw in (dict(width=100, height=128), dict(width=128, height=130), dict(width=128, height=128, filter_type=9),
+               dict(width=128, height=128, filter_type=5, kernel_idx=3), dict(width=128, height=128, slots=0),
+               dict(width=128, height=128, emit=0), dict(width=128, height=128, top_k=3), dict(width=128, height=128, bit_depth=9),
+               dict(width=128 * 300, height=128 * 200)):
+        with pytest.raises(mip.MipError) as ei:
+            mip.Engine(**kw)
+        assert ei.value.code == -1, (kw, str(ei.value))
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(mip.MipError) as ei:
+            mip.Engine(128, 128)
+        assert ei.value.code == -3 and "no CPU fallback" in str(ei.value)

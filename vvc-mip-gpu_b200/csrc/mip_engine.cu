@@ -78,6 +78,8 @@ static int check_cfg(const mipb200_config* c) {
     if (!c) return fail(MIPB200_EINVAL, "config is NULL");
     if (c->width < 8 || c->height < 4 || c->width % 8 != 0 || c->height % 4 != 0)
         return fail(MIPB200_EINVAL, "unsupported resolution %dx%d (need width %% 8 == 0, height %% 4 == 0)", c->width, c->height);
+    if ((long long)mipb200_num_ctus(c->width, c->height) * MIP_COSTS_PER_CTU > 0xffffffffll)
+        return fail(MIPB200_EINVAL, "frame %dx%d has more than 43 897 CTUs (the cost index is 32-bit)", c->width, c->height);
     if (c->filter_type < 0 || c->filter_type > 8) return fail(MIPB200_EINVAL, "filter_type %d out of range 0..8", c->filter_type);
     if (c->filter_type > 0) {
         const int nk = c->filter_type >= 5 ? 3 : 5;
