@@ -185,3 +185,31 @@ def test_topk_argument_checks(mip, tmp_path):
     assert r.returncode == 1 and "TopK needs --DecisionsLog" in r.stdout
     r = _run(mip, "-f", "1", "-s", "128x128", "-o", "x.u16", "--TopK=40", "--DecisionsLog=d.csv")
     assert r.returncode == 1 and "TopK must be in 1..12" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_binary_log_and_threaded_text_log(mip, oracle, tmp_path):
+    """--BinaryLog holds every frame's raw table (frames sharded over two workers land at their POC offset); the text log,
+    formatted CTU-parallel, is byte-identical to a single pass over the same table."""
+    from mipb200 import frames, tables as T
+    W, H, N = 640, 384, 3                                    # 15 CTUs: more than one round of formatter threads on small boxes
+    fs = [frames.natural_frame(W, H, 300 + i) for i in range(N)]
+    raw = tmp_path / "in.u16"
+    np.stack(fs).astype("<u2").tofile(str(raw))
+    dump = tmp_path / "costs.bin"
+    pre = tmp_path / "log"
+    r = _run(mip, "-f", str(N), "-s", f"{W}x{H}", "-o", str(raw), "--InputFormat=u16", "-l", str(pre), f"--BinaryLog={dump}", "--NumGpus=1",
+             "--UseAlternativeSamples=1", "--FilterType=filterFrame_2d_int_quarterCtu", "--KernelIdx=3", "--Compat")
+    assert r.returncode == 0, r.stdout + r.stderr
+    hdr, costs = frames.read_cost_dump(str(dump))
+    assert hdr == dict(version=1, width=W, height=H, frames=N, n_ctus=15, costs_per_ctu=97840, bit_depth=10, filter_type=3, kernel_idx=3)
+    for poc in range(N):
+        assert np.array_equal(costs[poc], oracle.run_frame(fs[poc], 3, 3)), poc
+    # text log of frame 0: header + 15 x 97840 lines, in CTU / type / CU / mode order with the right cost in the last column
+    lines = open(str(pre) + ".csv").read().splitlines()
+    assert lines[0] == "CTU,cuSizeName,W,H,CU,X,Y,Mode,SAD,SATD,minSadHad" and len(lines) - 1 == 15 * 97840
+    last = np.array([int(x[x.rfind(",") + 1:]) for x in lines[1:]], dtype=np.int32).reshape(15, 97840)
+    assert np.array_equal(last, costs[0])
+    ctu_col = np.array([int(x[:x.find(",")]) for x in lines[1::97840]])
+    assert ctu_col.tolist() == list(range(15))
+    assert lines[1 + 14 * 97840].startswith("14,ALL_AL_64x64,64,64,0,512,256,0,0,0,")

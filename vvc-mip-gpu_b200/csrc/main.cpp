@@ -15,17 +15,22 @@
 // --Compat (print 0 in the SAD/SATD columns like the reference's MAX_PERFORMANCE_DIST build),
 // --NoLog (skip the text log), --InputFormat csv|u16|yuv420p|yuv420p10le (binary luma input instead of
 // the 2 M stoi() calls per 1080p frame), --DecisionsLog FILE (per-CU best mode + cost of EVERY frame,
-// keyed by POC,X,Y,W,H: the table an encoder-side consumer ingests).
+// keyed by POC,X,Y,W,H: the table an encoder-side consumer ingests), --TopK k (shortlists in that log),
+// --BinaryLog FILE (raw int32 cost tables of every frame), --BitDepth 8|10|12, --Energy (NVML joules per frame),
+// --StageStamps 0|1 (the reference's TRACE_POWER stamps).
 //
 // The device work goes through the C ABI of include/mipb200.h only.
 #include <errno.h>
+#include <fcntl.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
 #include <time.h>
+#include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -56,15 +61,15 @@ struct Options {
     int topK = 0;
     int bitDepth = 10;
     int stageStamps = -1;   // -1: follow TRACE_POWER when one GPU is used
-    std::string inputFormat = "csv", decisionsLog;
+    std::string inputFormat = "csv", decisionsLog, binaryLog;
     bool allFrames = false, compat = false, noLog = false, help = false, energy = false;
 };
 
 const char* kLongOpts[] = {"help", "DeviceIndex", "FramesToBeEncoded", "Resolution", "OriginalFrames", "OutputPreffix",
                            "FilterType", "KernelIdx", "UseAlternativeSamples", "NumGpus", "AllFrames", "Compat", "NoLog",
-                           "InputFormat", "DecisionsLog", "TopK", "Energy", "StageStamps", "BitDepth"};
+                           "InputFormat", "DecisionsLog", "TopK", "Energy", "StageStamps", "BitDepth", "BinaryLog"};
 const bool kTakesValue[] = {false, true, true, true, true, true, true, true, true, true, false, false, false, true, true,
-                            true, false, true, true};
+                            true, false, true, true, true};
 constexpr int kNumOpts = sizeof(kLongOpts) / sizeof(kLongOpts[0]);
 
 void print_help() {
@@ -82,6 +87,7 @@ void print_help() {
            "  --AllFrames --Compat --NoLog   log every frame / zero SAD,SATD columns / no text log\n"
            "  --InputFormat arg (=csv)       csv | u16 (raw little-endian luma) | yuv420p | yuv420p10le\n"
            "  --DecisionsLog arg             write POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost for every frame\n"
+           "  --BinaryLog arg                write every frame's cost table as raw int32 (64-byte header, see INTEGRATION.md)\n"
            "  --TopK arg (=1)                with --DecisionsLog: the k cheapest modes per CU (adds Mode2,Cost2,... columns)\n"
            "  --Energy                       report joules per frame from the board's NVML energy counter\n"
            "  --BitDepth arg (=10)           8 | 10 | 12; 10 is the reference's pipeline (also for 8-bit content taken as is)\n"
@@ -162,6 +168,7 @@ bool parse_args(int argc, char** argv, Options& o) {
             case 16: o.energy = true; break;
             case 17: ok = to_int(val, &o.stageStamps); break;
             case 18: ok = to_int(val, &o.bitDepth); break;
+            case 19: o.binaryLog = val; break;
         }
         if (!ok) { fprintf(stderr, "the argument ('%s') for option '--%s' is invalid\n", val.c_str(), kLongOpts[opt]); return false; }
     }
@@ -265,12 +272,15 @@ bool read_frames_binary(const std::string& path, const std::string& fmt, int W, 
 
 // ---- cost log (main_aux_functions.h:735-798)
 struct LogBuf {
-    FILE* f;
+    FILE* f;                 // nullptr: memory only (the buffer grows; a formatter thread's private buffer)
     std::vector<char> b;
     size_t n = 0;
-    explicit LogBuf(FILE* fp) : f(fp), b(8u << 20) {}
-    void flush() { if (n) fwrite(b.data(), 1, n, f); n = 0; }
-    void ensure(size_t k) { if (n + k > b.size()) flush(); }
+    explicit LogBuf(FILE* fp, size_t cap = 8u << 20) : f(fp), b(cap) {}
+    void flush() { if (n && f) fwrite(b.data(), 1, n, f); if (f) n = 0; }
+    void ensure(size_t k) {
+        if (n + k <= b.size()) return;
+        if (f) flush(); else b.resize(b.size() * 2 + k);
+    }
     void put(const char* s, size_t k) { memcpy(b.data() + n, s, k); n += k; }
     void put_int(long v) {
         char t[24];
@@ -284,9 +294,9 @@ struct LogBuf {
 };
 
 void write_frame_log(LogBuf& lb, long poc, bool withPoc, const int32_t* cost, const int32_t* sad, const int32_t* satd,
-                     int nCtus, int W, bool compat) {
+                     int ctuBegin, int ctuEnd, int W, bool compat) {
     const int ctuCols = (W + 127) / 128;
-    for (int ctu = 0; ctu < nCtus; ++ctu) {
+    for (int ctu = ctuBegin; ctu < ctuEnd; ++ctu) {
         const int ctuX = 128 * (ctu % ctuCols), ctuY = 128 * (ctu / ctuCols);
         for (int t = 0; t < MIP_NUM_TYPES; ++t) {   // SizeId 2 types, then SizeId 1, then 4x4: the table order
             const mip_cu_type_t& ty = MIP_TYPES[t];
@@ -345,7 +355,10 @@ struct Shared {
     std::vector<std::vector<int32_t>> keepBest;
     std::atomic<int> errors{0};
     bool stamps = false;
+    int binFd = -1;                                                 // --BinaryLog
 };
+
+constexpr int kBinHeader = 64;   // "MIPB200C", then u32 version, width, height, frames, CTUs, costs per CTU, bit depth, filter type, kernel index
 
 // Engine of GPU g: context, streams, pinned rings, tables.  Runs before the timed window, like the reference's
 // platform / queue / buffer / program setup (main.cpp:87-549).
@@ -356,8 +369,8 @@ mipb200_engine* create_engine(Shared* sh, int g, mipb200_config* cfg_out) {
     cfg.filter_type = sh->filterType; cfg.kernel_idx = o.kernelIdx; cfg.slots = 3;
     cfg.top_k = o.topK > 1 ? o.topK : 0;
     cfg.bit_depth = o.bitDepth;
-    const bool wantLog = !o.noLog, wantDec = !o.decisionsLog.empty();
-    cfg.emit = (wantLog || !wantDec ? MIPB200_EMIT_COSTS : 0) | (wantLog && !o.compat ? MIPB200_EMIT_SAD_SATD : 0) |
+    const bool wantLog = !o.noLog, wantDec = !o.decisionsLog.empty(), wantBin = !o.binaryLog.empty();
+    cfg.emit = (wantLog || wantBin || !wantDec ? MIPB200_EMIT_COSTS : 0) | (wantLog && !o.compat ? MIPB200_EMIT_SAD_SATD : 0) |
                (wantDec ? MIPB200_EMIT_DECISIONS : 0);
     mipb200_engine* e = nullptr;
     if (mipb200_create(&e, &cfg) != 0) {
@@ -379,6 +392,16 @@ void gpu_worker(Shared* sh, mipb200_engine* e, mipb200_config cfg, int g, int G)
         mipb200_result r;
         if (mipb200_collect(e, &r) != 0) { fprintf(stderr, "[!] ERROR (GPU %d): %s\n", cfg.device, mipb200_last_error()); sh->errors++; return false; }
         const int poc = (int)r.poc;
+        if (sh->binFd >= 0) {   // raw table straight from the pinned ring to its place in the file (pwrite: any frame order, any thread)
+            const char* src = reinterpret_cast<const char*>(r.cost);
+            size_t left = ncost * sizeof(int32_t);
+            off_t off = (off_t)kBinHeader + (off_t)poc * (off_t)left;
+            while (left) {
+                const ssize_t w = pwrite(sh->binFd, src, left, off);
+                if (w <= 0) { perror("error while writing the binary log"); sh->errors++; return false; }
+                src += w; off += w; left -= (size_t)w;
+            }
+        }
         if (wantLog && (poc == 0 || o.allFrames)) {   // the reference exports frame 0 only (main.cpp:1268)
             memcpy(sh->keepCost[poc].data(), r.cost, ncost * sizeof(int32_t));
             if (r.sad) { memcpy(sh->keepSad[poc].data(), r.sad, ncost * sizeof(int32_t)); memcpy(sh->keepSatd[poc].data(), r.satd, ncost * sizeof(int32_t)); }
@@ -513,6 +536,15 @@ int main(int argc, char** argv) {
             if (!o.decisionsLog.empty()) { sh.keepMode[poc].resize(ncu); sh.keepBest[poc].resize(ncu); }
         }
     }
+    if (!o.binaryLog.empty()) {
+        sh.binFd = open(o.binaryLog.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+        if (sh.binFd < 0) { perror("error while opening the binary log"); destroy_all(); return 1; }
+        uint32_t hdr[kBinHeader / 4] = {0};
+        memcpy(hdr, "MIPB200C", 8);
+        hdr[2] = 1; hdr[3] = (uint32_t)W; hdr[4] = (uint32_t)H; hdr[5] = (uint32_t)o.nFrames; hdr[6] = (uint32_t)sh.nCtus;
+        hdr[7] = MIP_COSTS_PER_CTU; hdr[8] = (uint32_t)o.bitDepth; hdr[9] = (uint32_t)sh.filterType; hdr[10] = (uint32_t)o.kernelIdx;
+        if (pwrite(sh.binFd, hdr, sizeof(hdr), 0) != (ssize_t)sizeof(hdr)) { perror("error while writing the binary log"); destroy_all(); return 1; }
+    }
     // page-lock the frames so that every upload is a DMA from where the samples already are (no staging copy)
     const bool pinned = mipb200_pin_host(frames.data(), frames.size() * sizeof(uint16_t)) == 0;
     print_timestamp("FINISH BUILD KERNELS");
@@ -536,6 +568,7 @@ int main(int argc, char** argv) {
     for (int g = 0; g < o.numGpus && haveEnergy; ++g)
         if (mipb200_device_energy_mj(o.deviceIndex + g, &mj1[g]) != 0) haveEnergy = false;
     destroy_all();
+    if (sh.binFd >= 0) close(sh.binFd);
     if (pinned) mipb200_unpin_host(frames.data());
     if (sh.errors) return 1;
 
@@ -547,10 +580,25 @@ int main(int argc, char** argv) {
         LogBuf lb(f);
         const char* hdr = o.allFrames ? "POC,CTU,cuSizeName,W,H,CU,X,Y,Mode,SAD,SATD,minSadHad\n" : "CTU,cuSizeName,W,H,CU,X,Y,Mode,SAD,SATD,minSadHad\n";
         lb.put(hdr, strlen(hdr));
-        for (int poc = 0; poc < (o.allFrames ? o.nFrames : 1); ++poc)
-            write_frame_log(lb, poc, o.allFrames, sh.keepCost[poc].data(), sh.keepSad[poc].empty() ? nullptr : sh.keepSad[poc].data(),
-                            sh.keepSatd[poc].empty() ? nullptr : sh.keepSatd[poc].data(), sh.nCtus, W, o.compat);
         lb.flush();
+        // 13.2 M lines per 1080p frame: CTUs are formatted by all host threads into private buffers (one CTU = 4.4 MB of
+        // text each) and written in CTU order
+        const int nth = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<LogBuf> parts;
+        for (int t = 0; t < nth; ++t) parts.emplace_back(nullptr, 6u << 20);
+        for (int poc = 0; poc < (o.allFrames ? o.nFrames : 1); ++poc) {
+            const int32_t* cst = sh.keepCost[poc].data();
+            const int32_t* sd = sh.keepSad[poc].empty() ? nullptr : sh.keepSad[poc].data();
+            const int32_t* st = sh.keepSatd[poc].empty() ? nullptr : sh.keepSatd[poc].data();
+            for (int c0 = 0; c0 < sh.nCtus; c0 += nth) {
+                const int cnt = std::min(nth, sh.nCtus - c0);
+                std::vector<std::thread> th;
+                for (int t = 0; t < cnt; ++t)
+                    th.emplace_back([&, t] { parts[t].n = 0; write_frame_log(parts[t], poc, o.allFrames, cst, sd, st, c0 + t, c0 + t + 1, W, o.compat); });
+                for (auto& x : th) x.join();
+                for (int t = 0; t < cnt; ++t) fwrite(parts[t].b.data(), 1, parts[t].n, f);
+            }
+        }
         fclose(f);
     }
 

@@ -92,3 +92,18 @@ def read_csv(path: str, width: int, height: int, n_frames: int) -> np.ndarray:
                 vals = f.readline().split(",")[:width]
                 out[i, r] = np.array(vals, dtype=np.int64).astype(np.uint16)
     return out
+
+
+def read_cost_dump(path: str):
+    """Reads a `mipb200_main --BinaryLog` file -> (header dict, int32 costs [frames][nCTU][97840]).
+    Layout: 64-byte header = "MIPB200C", then little-endian u32 version, width, height, frames, CTUs, costs per CTU,
+    bit depth, filter type, kernel index (rest zero); then the tables frame by frame in POC order."""
+    with open(path, "rb") as f:
+        raw = f.read(64)
+        if len(raw) != 64 or raw[:8] != b"MIPB200C":
+            raise ValueError(f"{path} is not a mipb200 cost dump")
+        v = np.frombuffer(raw[8:48], dtype="<u4")
+        hdr = dict(version=int(v[0]), width=int(v[1]), height=int(v[2]), frames=int(v[3]), n_ctus=int(v[4]), costs_per_ctu=int(v[5]),
+                   bit_depth=int(v[6]), filter_type=int(v[7]), kernel_idx=int(v[8]))
+        data = np.fromfile(f, dtype="<i4")
+    return hdr, data.reshape(hdr["frames"], hdr["n_ctus"], hdr["costs_per_ctu"])
