@@ -688,7 +688,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         if (wi >= wcnt) return make_uint2(0xffffffffu, 0u);
         return __ldg(&g_lane[half][wbeg + wi][lane]);
     };
-    uint2 lr = draw((__ldg(&g_lane[half][wbeg][lane]).y >> 30) << 2);
+    uint2 lr = draw((__ldg(&g_lane[half][min(wbeg, MAX_WORK - 1)][lane]).y >> 30) << 2);
     while (lr.x != 0xffffffffu) {
         const uint2 lr_next = draw((lr.y >> 30) << 2);
         // warp task = 32 consecutive (CU, mode) pairs of one type: a warp touches at most 3-4 CUs, so the shared-memory
