@@ -37,7 +37,7 @@ def cpu_ref():
 def test_2d_int_filters_equal_the_references_cpu_filters(oracle, cpu_ref, taps, ft, kidxs):
     from mipb200 import frames
     cases = [frames.noise_frame(256, 136, 5), frames.natural_frame(384, 128, 6), frames.extreme_frame(128, 128, 2),
-             frames.impulse_frame(192, 72, 7)]
+             frames.impulse_frame(192, 72, 7), frames.natural_frame(1920, 1080, 8)]
     for f in cases:
         for k in kidxs:
             want = cpu_ref(f, taps, k)
