@@ -95,3 +95,27 @@ def test_filter_fusion_exactness_sweep_1080p(mip, oracle):
         with mip.Engine(1920, 1080, filter_type=ft, kernel_idx=k, slots=1, emit=mip.EMIT_COSTS) as eng:
             got = eng.run(f).cost.copy()
         _eq(got, oracle.run_frame(f, ft, k), f"frame {i % 16} filter_type={ft} kernel_idx={k}")
+
+
+@pytest.mark.parametrize("bits,ft,kidx", [(12, 7, 2), (8, 2, 3)])
+def test_1080p_other_bit_depths_with_shortlists(mip, oracle, bits, ft, kidx):
+    """The 8- and 12-bit pipelines and the top-5 shortlist at the BASELINE size: cost, SAD, SATD, decisions and shortlist
+    against the oracle (noise uses the whole sample range, so the clamps at 0 and (1 << bits) - 1 are exercised)."""
+    from mipb200 import frames
+    f = frames.noise_frame(1920, 1080, 900 + bits, bits=bits)
+    with mip.Engine(1920, 1080, filter_type=ft, kernel_idx=kidx, slots=1, bit_depth=bits, top_k=5,
+                    emit=mip.EMIT_COSTS | mip.EMIT_SAD_SATD | mip.EMIT_DECISIONS) as eng:
+        r = eng.run(f)
+        got = [a.copy() for a in (r.cost, r.sad, r.satd, r.best_mode, r.best_cost, r.topk_mode, r.topk_cost)]
+    cost, sad, satd = oracle.run_frame(f, ft, kidx, want_sad_satd=True, bit_depth=bits)
+    _eq(got[0], cost, f"{bits}-bit 1080p cost")
+    _eq(got[1], sad, f"{bits}-bit 1080p sad")
+    _eq(got[2], satd, f"{bits}-bit 1080p satd")
+    bm, bc = oracle.decisions(cost)
+    _eq(got[3], bm, "best_mode")
+    _eq(got[4], bc, "best_cost")
+    tm, tc = oracle.topk(cost, 5)
+    _eq(got[5], tm, "topk_mode")
+    _eq(got[6], tc, "topk_cost")
+    ok = cost != -1
+    assert np.array_equal(cost[ok], np.minimum(2 * sad[ok], satd[ok]))          # intra.cl:1166
