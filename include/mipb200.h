@@ -123,7 +123,7 @@ int mipb200_run_device(mipb200_engine* e, const uint16_t* d_frame, int32_t* d_co
  * referenceFrame, filteredFrame, frameWidth, frameHeight, kernelIdx). */
 int mipb200_filter_device(mipb200_engine* e, const uint16_t* d_frame, uint16_t* d_out, void* stream);
 
-/* Per CU argmin over an existing cost table (device pointers). */
+/* Per CU argmin over an existing cost table (device pointers; d_cost 16-byte aligned). */
 int mipb200_decide_device(mipb200_engine* e, const int32_t* d_cost, uint8_t* d_best_mode,
                           int32_t* d_best_cost, void* stream);
 
