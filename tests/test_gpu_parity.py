@@ -290,3 +290,20 @@ def test_random_geometries(mip, oracle):
             bm, bc = oracle.decisions(want[0])
             _assert_same(r.best_mode, bm, tag + " best_mode")
             _assert_same(r.best_cost, bc, tag + " best_cost")
+
+
+@pytest.mark.parametrize("shape", [(8, 4), (8, 8), (16, 4), (8, 64), (64, 4), (128, 4), (8, 128), (136, 132), (24, 20)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_tiny_frames(mip, oracle, shape):
+    """Frames smaller than the TMA box (144x69) down to the smallest legal one (8x4: two 4x4 CUs and one 8x4 CU fit)."""
+    from mipb200 import frames
+    w, h = shape
+    for ft in (0, 3, 6):
+        f = frames.noise_frame(w, h, w * 1000 + h)
+        want = oracle.run_frame(f, ft, 1)
+        assert (want != -1).any()
+        with mip.Engine(w, h, filter_type=ft, kernel_idx=1, slots=1, emit=mip.EMIT_COSTS | mip.EMIT_DECISIONS) as eng:
+            r = eng.run(f)
+            _assert_same(r.cost, want, f"{w}x{h} ft={ft} cost")
+            bm, bc = oracle.decisions(want)
+            _assert_same(r.best_mode, bm, "best_mode")
+            _assert_same(r.best_cost, bc, "best_cost")
