@@ -198,7 +198,9 @@ def test_cli_binary_log_and_threaded_text_log(mip, oracle, tmp_path):
     np.stack(fs).astype("<u2").tofile(str(raw))
     dump = tmp_path / "costs.bin"
     pre = tmp_path / "log"
-    r = _run(mip, "-f", str(N), "-s", f"{W}x{H}", "-o", str(raw), "--InputFormat=u16", "-l", str(pre), f"--BinaryLog={dump}", "--NumGpus=1",
+    import torch
+    g = 2 if torch.cuda.device_count() >= 2 else 1
+    r = _run(mip, "-f", str(N), "-s", f"{W}x{H}", "-o", str(raw), "--InputFormat=u16", "-l", str(pre), f"--BinaryLog={dump}", f"--NumGpus={g}",
              "--UseAlternativeSamples=1", "--FilterType=filterFrame_2d_int_quarterCtu", "--KernelIdx=3", "--Compat")
     assert r.returncode == 0, r.stdout + r.stderr
     hdr, costs = frames.read_cost_dump(str(dump))
