@@ -14,9 +14,9 @@ hot path (filter -> MIP costs -> decisions) over a batch of B distinct frames pe
   e2e    frames/s through the C ABI host path: host frames -> pinned ring -> H2D -> kernels -> D2H of
          the MIP decisions (best mode + its cost for every CU); e2e_costs additionally reads back the
          full int32 cost table (the reference's minSadHad readback, 52.8 MB per 1080p frame)
-  roofline      HBM view of the fused cost kernel (algorithmic bytes / kernel time / measured
-                copy bandwidth); the path is INT32-issue bound, so `int32` carries the
-                compute view (algorithmic INT32 ops)
+  roofline      the fused cost kernel against the binding roof: INT32 issue (algorithmic INT32 ops of
+                BASELINE.md section 2 / kernel time / measured INT32 peak); the HBM view (algorithmic
+                bytes / kernel time / measured copy bandwidth) is nested as roofline.hbm
   cpu_baseline  the CPU oracle (port of the reference algorithm, OpenMP, all host cores) on a
                 bounded sample of the same workload (rank 0, N == 1 only)
 
@@ -355,18 +355,19 @@ def main():
                           "result": "decisions + the full int32 cost table (the reference's minSadHad readback, 52.8 MB per frame)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "mip_cost_kernel", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel_ms_per_frame": kernel_ms,
-                         "note": "path is INT32-issue bound (BASELINE.md section 2); see int32"},
-            # frac: the kernel alone, launches back to back on one stream (each launch pays its own ramp-up and tail);
-            # frac_timed_region: the same launches inside the timed region, where frames overlap on the slot streams
-            # (timed-region time / launches: what one launch costs the GPU in steady state)
-            "int32": {"achieved_tops": OPS_PER_FRAME / (kernel_ms * 1e-3) / 1e12, "peak_tops": int32_peak,
-                      "frac": OPS_PER_FRAME / (kernel_ms * 1e-3) / 1e12 / int32_peak, "peak_source": int32_src,
-                      "ops_per_frame": OPS_PER_FRAME,
-                      "ms_per_launch_timed_region": dev_ms / max(1, launches),
-                      "frac_timed_region": OPS_PER_FRAME * value / world / 1e12 / int32_peak},
+            # BASELINE.json's metric asks for the fraction of the SLOWER of the INT32-issue and HBM rooflines.  This path is
+            # INT32-issue bound (50-90x further from the HBM roof), so `roofline` is the INT32 view and the HBM view rides
+            # inside it.  frac: the kernel alone, launches back to back on one stream (each launch pays its own ramp-up
+            # and tail); frac_timed_region: the same launches inside the timed region, where frames overlap on the slot
+            # streams (timed-region time / launches = what one launch costs the GPU in steady state).
+            "roofline": {"bound": "int32", "kernel": "mip_cost_kernel",
+                         "achieved": OPS_PER_FRAME / (kernel_ms * 1e-3) / 1e12, "peak": int32_peak, "unit": "Tops/s",
+                         "frac": OPS_PER_FRAME / (kernel_ms * 1e-3) / 1e12 / int32_peak,
+                         "frac_timed_region": OPS_PER_FRAME * value / world / 1e12 / int32_peak,
+                         "traffic": traffic, "ops_per_launch": OPS_PER_FRAME, "peak_source": int32_src,
+                         "kernel_ms_per_frame": kernel_ms, "ms_per_launch_timed_region": dev_ms / max(1, launches),
+                         "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME, "peak_source": peak_src}},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
