@@ -111,7 +111,7 @@ int mipb200_num_ctus(int width, int height);
 /* Device-resident path: the frame is already in HBM and the results stay there (no host
  * copies).  All pointers are device pointers on the engine's GPU; any output may be NULL.
  * `stream` is a cudaStream_t (NULL = the engine's compute stream).  Asynchronous.  d_cost may be NULL when only the
- * decisions are wanted; d_best_mode and d_best_cost go together; d_frame must be 16-byte aligned (TMA source).
+ * decisions are wanted; d_best_mode and d_best_cost go together, and so do d_sad and d_satd; d_frame must be 16-byte aligned (TMA source).
  * ONE kernel: this is the fused equivalent of the reference's kernel sequence filterFrame_* ->
  * initBoundaries -> MIP_ReducedPred -> upsampleDistortion x3 (main.cpp:723-742, 819-844,
  * 925-946, 1011-1045, 1090-1124, 1167-1200). */

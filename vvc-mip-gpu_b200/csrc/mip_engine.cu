@@ -291,6 +291,7 @@ MIPB200_API int mipb200_run_device(mipb200_engine* e, const uint16_t* d_frame, i
     if (!e || !d_frame) return fail(MIPB200_EINVAL, "engine and d_frame are required");
     if (!d_cost && !d_best_mode) return fail(MIPB200_EINVAL, "at least one of d_cost and d_best_mode/d_best_cost is required");
     if ((d_best_mode == nullptr) != (d_best_cost == nullptr)) return fail(MIPB200_EINVAL, "d_best_mode and d_best_cost go together");
+    if ((d_sad == nullptr) != (d_satd == nullptr)) return fail(MIPB200_EINVAL, "d_sad and d_satd go together");
     CU_TRY(cudaSetDevice(e->cfg.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
     return enqueue_kernels(e, d_frame, d_cost, d_sad, d_satd, d_best_mode, d_best_cost, st);

@@ -61,15 +61,17 @@ constexpr int RED_WORDS = 32;           // packed reduced-prediction words per t
 // different matrices at the same row: the per-matrix pads spread the matrices over distinct banks, and each permuted
 // copy starts a whole number of bank groups after the plain one (48 B / 64 B / 64 B modulo 128), so plain and transposed
 // lanes never collide either.
-constexpr int M2_STRIDE = 528, M1_STRIDE = 144, M0_STRIDE = 68;   // 64x8 B + 16, 16x8 B + 16, 16x4 B + 4
+constexpr int M2_STRIDE = 528, M1_STRIDE = 144, M0_STRIDE = 80;   // 64x8 B + 16, 16x8 B + 16, 16x4 B + 16
 constexpr int M2_OFF = 0, M2T_OFF = M2_OFF + 6 * M2_STRIDE;       // 3168 = 24*128 + 96
 constexpr int M1_OFF = M2T_OFF + 6 * M2_STRIDE, M1T_OFF = M1_OFF + 8 * M1_STRIDE;    // +1152 = 9*128
-constexpr int M0_OFF = M1T_OFF + 8 * M1_STRIDE, M0T_OFF = M0_OFF + 16 * M0_STRIDE;   // +1088 = 8*128 + 64
-constexpr int MAT_BYTES = M0T_OFF + 16 * M0_STRIDE;   // 10816
+constexpr int M0_OFF = M1T_OFF + 8 * M1_STRIDE, M0T_OFF = M0_OFF + 16 * M0_STRIDE;   // +1280
+constexpr int MAT_BYTES = M0T_OFF + 16 * M0_STRIDE;   // 11200
 // sizeId 2 / 1: two 8-byte rows per LDS.128, so matrices start 16-byte aligned and 4 banks apart (6 + 6 or 8 + 8 matrices
-// of a warp = 12 or 16 distinct 16-byte rows = the minimum of 2 wavefronts); sizeId 0: 4-byte rows, 1 bank apart.
-static_assert(M2_STRIDE % 16 == 0 && M1_STRIDE % 16 == 0 && M2T_OFF % 16 == 0 && M1_OFF % 16 == 0 && M1T_OFF % 16 == 0, "LDS.128 alignment");
-static_assert((M2_STRIDE / 4) % 32 == 4 && (M1_STRIDE / 4) % 32 == 4 && (M0T_OFF - M0_OFF) % 128 == 64, "bank phases");
+// of a warp = 12 or 16 distinct 16-byte rows = the minimum of 2 wavefronts); sizeId 0: four 4-byte rows per LDS.128, the
+// 16 + 16 matrices of a warp 20 banks apart = 8 distinct 4-bank groups used by 4 matrices each = the minimum of 4 wavefronts.
+static_assert(M2_STRIDE % 16 == 0 && M1_STRIDE % 16 == 0 && M0_STRIDE % 16 == 0 && M2T_OFF % 16 == 0 && M1_OFF % 16 == 0 &&
+              M1T_OFF % 16 == 0 && M0_OFF % 16 == 0 && M0T_OFF % 16 == 0, "LDS.128 alignment");
+static_assert((M2_STRIDE / 4) % 32 == 4 && (M1_STRIDE / 4) % 32 == 4 && (M0_STRIDE / 4) % 8 == 4, "bank phases");
 
 constexpr int SM_RED = 0;                                      // first: the TMA box lands here (128-byte aligned)
 constexpr int SM_RED_BYTES = RED_WORDS * NT * 4;               // 49152 at NT = 384
@@ -339,15 +341,17 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
         const uint8_t* mb = c.s_mat + (tr ? M0T_OFF : M0_OFF) + mat * M0_STRIDE;   // row = output position, also for transposed modes
         int p[16];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a) {
+            const int4 cw4 = *reinterpret_cast<const int4*>(mb + a * 16);      // the 4 taps of output samples 4a .. 4a+3
+            const int cw[4] = {cw4.x, cw4.y, cw4.z, cw4.w};
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const int cw = *reinterpret_cast<const int*>(mb + (a * 4 + b) * 4);
                 int acc = acc0;
-                acc = __dp2a_lo(ipk[0], cw, acc);
-                acc = __dp2a_hi(ipk[1], cw, acc);
+                acc = __dp2a_lo(ipk[0], cw[b], acc);
+                acc = __dp2a_hi(ipk[1], cw[b], acc);
                 p[a * 4 + b] = clamp_px(acc >> 6, c.maxv);
             }
+        }
         int d[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -730,18 +734,29 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             const uint32_t o = ctuBase + coff;
             const int cost = min(2 * sad, satd);            // intra.cl:1166
             if (g_cost) g_cost[o] = active ? cost : -1;
-            if (g_sad) g_sad[o] = active ? sad : -1;
-            if (g_satd) g_satd[o] = active ? satd : -1;
+            if (g_sad) { g_sad[o] = active ? sad : -1; g_satd[o] = active ? satd : -1; }   // both or neither (launch_costs)
         }
         if (g_best_mode) {
             // decision = argmin over the CU's modes, lowest mode wins ties: min of (cost << 6 | mode), cost < 2^24.
             // The lanes of one CU are first reduced in registers (MATCH.ANY + REDUX.MIN), then one lane per CU does the
             // shared-memory atomicMin: 3-4 distinct addresses per warp instead of 32 lanes serialising on them.
             const bool vote = inRange && part == 0 && active;
-            const unsigned grp = __match_any_sync(0xffffffffu, vote ? slot : -1 - lane);
-            if (vote) {
-                const uint32_t best = __reduce_min_sync(grp, ((uint32_t)min(2 * sad, satd) << 6) | (uint32_t)mode);
-                if (lane == __ffs(grp) - 1) atomicMin(&s_dec[slot - ordBeg], best);
+            const uint32_t key = ((uint32_t)min(2 * sad, satd) << 6) | (uint32_t)mode;
+            const int modes = ty.modes;
+            if (modes >= 16) {
+                // 16 or 32 modes: a CU is exactly one half or one whole warp task (in range, active and voting as a whole),
+                // so its group is known without MATCH and its slot has a single writer: a plain store
+                const unsigned grp = modes == 32 ? 0xffffffffu : ((lane & 16) ? 0xffff0000u : 0x0000ffffu);
+                if (vote) {
+                    const uint32_t best = __reduce_min_sync(grp, key);
+                    if ((lane & (modes - 1)) == 0) s_dec[slot - ordBeg] = best;
+                }
+            } else {
+                const unsigned grp = __match_any_sync(0xffffffffu, vote ? slot : -1 - lane);
+                if (vote) {
+                    const uint32_t best = __reduce_min_sync(grp, key);
+                    if (lane == __ffs(grp) - 1) atomicMin(&s_dec[slot - ordBeg], best);
+                }
             }
         }
         lr = lr_next;
@@ -1050,7 +1065,7 @@ cudaError_t make_filter_params(int ft, int kidx, int bit_depth, FilterParams* fp
 cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, int bit_depth, const FilterParams& fp, int32_t* d_cost, int32_t* d_sad,
                          int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, cudaStream_t st) {
     if (bit_depth != 8 && bit_depth != 10 && bit_depth != 12) return cudaErrorInvalidValue;
-    if ((d_best_mode == nullptr) != (d_best_cost == nullptr)) return cudaErrorInvalidValue;
+    if ((d_best_mode == nullptr) != (d_best_cost == nullptr) || (d_sad == nullptr) != (d_satd == nullptr)) return cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(d_frame) & 15) != 0) return cudaErrorMisalignedAddress;   // TMA needs a 16-byte aligned frame
     CUtensorMap map;
     cudaError_t e = make_frame_map(d_frame, W, H, &map);
