@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <mutex>
 #include <vector>
@@ -126,6 +127,12 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
     if (rc) return rc;
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
+    for (int attempt = 0; attempt < 10 && (ce == cudaErrorInitializationError || ce == cudaErrorDevicesUnavailable); ++attempt) {
+        // seen on a box where the previous process was still tearing its context down: transient, a short wait cures it
+        cudaGetLastError();
+        usleep(200 * 1000);
+        ce = cudaGetDeviceCount(&ndev);
+    }
     if (ce != cudaSuccess || ndev == 0)
         return fail(MIPB200_ENODEV, "no CUDA device: %s (this engine has no CPU fallback)", cudaGetErrorString(ce));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(MIPB200_ENODEV, "device %d not in 0..%d", cfg->device, ndev - 1);
