@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -85,3 +87,33 @@ def test_create_validates_the_configuration_before_touching_cuda(mip):
         with pytest.raises(mip.MipError) as ei:
             mip.Engine(128, 128)
         assert ei.value.code == -3 and "no CPU fallback" in str(ei.value)
+
+
+def _build_example(tmp_path):
+    import subprocess
+    exe = tmp_path / "minimal"
+    libdir = os.path.join(ROOT, "vvc-mip-gpu_b200", "lib")
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "minimal.c"),
+                    "-L", libdir, "-lmipb200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    return exe
+
+
+def test_plain_c_example_builds_and_refuses_to_run_without_a_gpu(mip, tmp_path):
+    """examples/minimal.c is C (not C++): it compiles against the header, links the library and -- on a box without a GPU --
+    reports the missing device instead of computing anything on the CPU."""
+    import subprocess
+    import torch
+    exe = _build_example(tmp_path)
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_example_runs(mip, tmp_path):
+    import subprocess
+    exe = _build_example(tmp_path)
+    r = subprocess.run([str(exe), "384", "264"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("frame ") == 8 and "8 kernel launches" in r.stdout
