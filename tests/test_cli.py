@@ -215,3 +215,20 @@ def test_cli_binary_log_and_threaded_text_log(mip, oracle, tmp_path):
     ctu_col = np.array([int(x[:x.find(",")]) for x in lines[1::97840]])
     assert ctu_col.tolist() == list(range(15))
     assert lines[1 + 14 * 97840].startswith("14,ALL_AL_64x64,64,64,0,512,256,0,0,0,")
+
+
+@pytest.mark.gpu
+def test_cli_bit_depth(mip, oracle, tmp_path):
+    """--BitDepth reaches the engine: a 12-bit frame's table equals the 12-bit oracle (and not the 10-bit one); bad values are refused."""
+    from mipb200 import frames
+    f = frames.noise_frame(256, 128, 77, bits=12)
+    raw = tmp_path / "in.u16"
+    f.astype("<u2").tofile(str(raw))
+    dump = tmp_path / "c.bin"
+    r = _run(mip, "-f", "1", "-s", "256x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", f"--BinaryLog={dump}", "--BitDepth=12")
+    assert r.returncode == 0, r.stdout + r.stderr
+    hdr, costs = frames.read_cost_dump(str(dump))
+    assert hdr["bit_depth"] == 12
+    assert np.array_equal(costs[0], oracle.run_frame(f, bit_depth=12)) and not np.array_equal(costs[0], oracle.run_frame(f, bit_depth=10))
+    r = _run(mip, "-f", "1", "-s", "256x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", "--BitDepth=9")
+    assert r.returncode == 1 and "BitDepth must be 8, 10 or 12" in r.stdout
