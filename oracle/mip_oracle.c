@@ -30,7 +30,10 @@
  * (OpenCL only).  The oracle is pinned against (1) the survey's known-answer vectors
  * (tests/golden/survey_kat.json), (2) outputs of the reference's own, unmodified OpenCL
  * kernels run on a B200 through NVIDIA's OpenCL driver by oracle/ocl_ref (fixtures under
- * tests/golden/, generating script committed).  See tests/test_oracle_golden.py.
+ * tests/golden/, generating scripts committed): six complete cost tables of small frames, all
+ * 32 filter outputs, and per-CTU hashes of the complete tables of three 1080p frames and one
+ * 2160p frame, and (3) the reference's own CPU filters compiled from its checkout
+ * (oracle/cpu_ref).  See tests/test_oracle_golden.py and tests/test_oracle_cpu_ref.py.
  */
 #include <stdint.h>
 #include <stdlib.h>
