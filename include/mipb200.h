@@ -108,6 +108,10 @@ int mipb200_collect(mipb200_engine* e, mipb200_result* out);
 int mipb200_in_flight(const mipb200_engine* e);
 int mipb200_num_ctus(int width, int height);
 
+/* Number of CUDA devices (>= 0), or a negative MIPB200_E* code.  Replaces the reference's platform / device scan
+ * (main.cpp:117-228: "COMPUTING ON GPU i" / "Incorrect GPU index. Only N GPUs are detected"). */
+int mipb200_device_count(void);
+
 /* Device-resident path: the frame is already in HBM and the results stay there (no host
  * copies).  All pointers are device pointers on the engine's GPU; any output may be NULL.
  * `stream` is a cudaStream_t (NULL = the engine's compute stream).  Asynchronous.  d_cost may be NULL when only the

@@ -232,3 +232,25 @@ def test_cli_bit_depth(mip, oracle, tmp_path):
     assert np.array_equal(costs[0], oracle.run_frame(f, bit_depth=12)) and not np.array_equal(costs[0], oracle.run_frame(f, bit_depth=10))
     r = _run(mip, "-f", "1", "-s", "256x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", "--BitDepth=9")
     assert r.returncode == 1 and "BitDepth must be 8, 10 or 12" in r.stdout
+
+
+def test_no_gpu_message_matches_the_reference(mip, tmp_path):
+    """On a box without a GPU the CLI says what the reference says when the device index is out of range (main.cpp:225-227)
+    and exits 0 like it; with a GPU the banner 'COMPUTING ON GPU i' appears instead (checked in the GPU tests)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    raw = tmp_path / "in.u16"
+    np.zeros((128, 128), dtype="<u2").tofile(str(raw))
+    r = _run(mip, "-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog")
+    assert r.returncode == 0 and "Incorrect GPU index. Only 0 GPUs are detected" in r.stdout
+
+
+@pytest.mark.gpu
+def test_gpu_selection_banner(mip, tmp_path):
+    raw = tmp_path / "in.u16"
+    np.zeros((128, 128), dtype="<u2").tofile(str(raw))
+    r = _run(mip, "-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog")
+    assert r.returncode == 0 and "COMPUTING ON GPU 0" in r.stdout
+    r = _run(mip, "-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", "--DeviceIndex=64")
+    assert r.returncode == 0 and "Incorrect GPU index. Only" in r.stdout and "TIMING RESULTS" not in r.stdout

@@ -514,6 +514,15 @@ int main(int argc, char** argv) {
     sh.keepMode.resize(o.nFrames); sh.keepBest.resize(o.nFrames);
 
     // ---- timed window: first upload -> last result resident on the host (main.cpp:566-569, 1247-1250)
+    {   // device selection banner of the reference (main.cpp:220-228); it exits with 0 on a bad index
+        const int found = mipb200_device_count();
+        if (found < 0) { fprintf(stderr, "[!] ERROR: %s\n", mipb200_last_error()); return 1; }
+        if (o.deviceIndex < 0 || o.deviceIndex + o.numGpus > found) {
+            printf("Incorrect GPU index. Only %d GPUs are detected\n", found);
+            return 0;
+        }
+        for (int g = 0; g < o.numGpus; ++g) printf("COMPUTING ON GPU %d\n", o.deviceIndex + g);
+    }
     // ---- set-up (not timed, like the reference's context / buffer / program creation)
     print_timestamp("START BUILD KERNELS");
     std::vector<mipb200_engine*> engines(o.numGpus, nullptr);

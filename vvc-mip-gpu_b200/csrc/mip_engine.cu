@@ -75,6 +75,25 @@ MIPB200_API const char* mipb200_last_error(void) { return g_err; }
 MIPB200_API const char* mipb200_version(void) { return "mipb200 0.1 (sm_100a)"; }
 MIPB200_API int mipb200_num_ctus(int w, int h) { return ((w + 127) / 128) * ((h + 127) / 128); }
 
+static cudaError_t device_count(int* n) {
+    cudaError_t ce = cudaGetDeviceCount(n);
+    for (int attempt = 0; attempt < 10 && (ce == cudaErrorInitializationError || ce == cudaErrorDevicesUnavailable); ++attempt) {
+        // seen on a box where the previous process was still tearing its context down: transient, a short wait cures it
+        cudaGetLastError();
+        usleep(200 * 1000);
+        ce = cudaGetDeviceCount(n);
+    }
+    return ce;
+}
+
+MIPB200_API int mipb200_device_count(void) {
+    int n = 0;
+    const cudaError_t ce = device_count(&n);
+    if (ce == cudaErrorNoDevice || ce == cudaErrorInsufficientDriver) { cudaGetLastError(); return 0; }
+    if (ce != cudaSuccess) return fail(MIPB200_ECUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(ce));
+    return n;
+}
+
 static int check_cfg(const mipb200_config* c) {
     if (!c) return fail(MIPB200_EINVAL, "config is NULL");
     if (c->width < 8 || c->height < 4 || c->width % 8 != 0 || c->height % 4 != 0)
@@ -126,13 +145,7 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
     int rc = check_cfg(cfg);
     if (rc) return rc;
     int ndev = 0;
-    cudaError_t ce = cudaGetDeviceCount(&ndev);
-    for (int attempt = 0; attempt < 10 && (ce == cudaErrorInitializationError || ce == cudaErrorDevicesUnavailable); ++attempt) {
-        // seen on a box where the previous process was still tearing its context down: transient, a short wait cures it
-        cudaGetLastError();
-        usleep(200 * 1000);
-        ce = cudaGetDeviceCount(&ndev);
-    }
+    const cudaError_t ce = device_count(&ndev);
     if (ce != cudaSuccess || ndev == 0)
         return fail(MIPB200_ENODEV, "no CUDA device: %s (this engine has no CPU fallback)", cudaGetErrorString(ce));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(MIPB200_ENODEV, "device %d not in 0..%d", cfg->device, ndev - 1);

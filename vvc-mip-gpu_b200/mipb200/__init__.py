@@ -32,7 +32,7 @@ TOPK_MAX = 12
 # every symbol include/mipb200.h declares (tests/test_abi.py checks the header against this)
 ABI_SYMBOLS = (
     "mipb200_create", "mipb200_destroy", "mipb200_next_input", "mipb200_submit", "mipb200_collect",
-    "mipb200_in_flight", "mipb200_num_ctus", "mipb200_run_device", "mipb200_filter_device",
+    "mipb200_in_flight", "mipb200_num_ctus", "mipb200_device_count", "mipb200_run_device", "mipb200_filter_device",
     "mipb200_decide_device", "mipb200_topk_device", "mipb200_kernel_launches", "mipb200_device_energy_mj", "mipb200_pin_host", "mipb200_unpin_host", "mipb200_sync", "mipb200_last_error",
     "mipb200_version",
 )
@@ -96,6 +96,8 @@ def lib() -> ctypes.CDLL:
         L.mipb200_in_flight.restype = ctypes.c_int
         L.mipb200_num_ctus.argtypes = [ctypes.c_int, ctypes.c_int]
         L.mipb200_num_ctus.restype = ctypes.c_int
+        L.mipb200_device_count.argtypes = []
+        L.mipb200_device_count.restype = ctypes.c_int
         L.mipb200_run_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
         L.mipb200_run_device.restype = ctypes.c_int
         L.mipb200_filter_device.argtypes = [vp, vp, vp, vp]
