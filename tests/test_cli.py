@@ -6,6 +6,8 @@ import subprocess
 import numpy as np
 import pytest
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def _cli(mip):
     if not os.path.exists(mip.CLI_PATH):
@@ -254,3 +256,14 @@ def test_gpu_selection_banner(mip, tmp_path):
     assert r.returncode == 0 and "COMPUTING ON GPU 0" in r.stdout
     r = _run(mip, "-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", "--DeviceIndex=64")
     assert r.returncode == 0 and "Incorrect GPU index. Only" in r.stdout and "TIMING RESULTS" not in r.stdout
+
+
+def test_log_writers_selftest(mip, tmp_path):
+    """tests/cli_writers_selftest.cpp: the CLI's buffered, thread-parallel formatters (cost log with and without POC / SAD /
+    SATD, decisions log with a top-3 shortlist) write byte for byte what plain fprintf loops write.  No GPU needed."""
+    libdir = os.path.join(ROOT, "vvc-mip-gpu_b200", "lib")
+    exe = tmp_path / "selftest"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", str(exe), os.path.join(ROOT, "tests", "cli_writers_selftest.cpp"),
+                    "-L", libdir, "-lmipb200", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "selftest: ok" in r.stdout, r.stdout + r.stderr

@@ -321,20 +321,24 @@ void write_frame_log(LogBuf& lb, long poc, bool withPoc, const int32_t* cost, co
 }
 
 // per-CU decisions of one frame: POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost[,Mode2,Cost2,...] (skipped CUs: 255,-1)
-// bm/bc hold k entries per CU in ascending (cost, mode) order.
-void write_decisions(LogBuf& lb, long poc, const uint8_t* bm, const int32_t* bc, int k, int nCtus, int W) {
+// bm/bc hold k entries per CU in ascending (cost, mode) order.  726 300 lines per 1080p frame: no printf in the CU loop.
+void write_decisions(LogBuf& lb, long poc, const uint8_t* bm, const int32_t* bc, int k, int ctuBegin, int ctuEnd, int W) {
     const int ctuCols = (W + 127) / 128;
-    for (int ctu = 0; ctu < nCtus; ++ctu) {
+    for (int ctu = ctuBegin; ctu < ctuEnd; ++ctu) {
         const int ctuX = 128 * (ctu % ctuCols), ctuY = 128 * (ctu / ctuCols);
         for (int t = 0; t < MIP_NUM_TYPES; ++t) {
             const mip_cu_type_t& ty = MIP_TYPES[t];
+            char mid[96];                                   // ",<type name>,<w>,<h>," is the same for every CU of the type
+            const int ml = snprintf(mid, sizeof(mid), ",%s,%d,%d,", ty.name, ty.w, ty.h);
             for (int cu = 0; cu < ty.n; ++cu) {
                 const size_t i = ((size_t)ctu * MIP_CUS_PER_CTU + ty.cu_off + cu) * k;
-                char pre[160];
-                const int pl = snprintf(pre, sizeof(pre), "%ld,%d,%s,%d,%d,%d,%d,%d", poc, ctu, ty.name, ty.w, ty.h, cu,
-                                        ctuX + ty.xs[cu % ty.cols], ctuY + ty.ys[cu / ty.cols]);
                 lb.ensure(512);
-                lb.put(pre, pl);
+                lb.put_int(poc); lb.b[lb.n++] = ',';
+                lb.put_int(ctu);
+                lb.put(mid, ml);
+                lb.put_int(cu); lb.b[lb.n++] = ',';
+                lb.put_int(ctuX + ty.xs[cu % ty.cols]); lb.b[lb.n++] = ',';
+                lb.put_int(ctuY + ty.ys[cu / ty.cols]);
                 for (int j = 0; j < k; ++j) {
                     lb.b[lb.n++] = ',';
                     lb.put_int(bm[i + j]); lb.b[lb.n++] = ',';
@@ -343,6 +347,23 @@ void write_decisions(LogBuf& lb, long poc, const uint8_t* bm, const int32_t* bc,
                 lb.b[lb.n++] = '\n';
             }
         }
+    }
+}
+
+// Runs fmt(buffer, item) for item = 0 .. n-1 on the host threads, each into a private memory buffer, and writes the
+// buffers to f in item order (items = CTUs of the cost log, frames of the decisions log).
+template <class Fmt>
+void format_parallel(FILE* f, int n, size_t bufBytes, Fmt fmt) {
+    const int nth = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<LogBuf> parts;
+    for (int t = 0; t < std::min(nth, n); ++t) parts.emplace_back(nullptr, bufBytes);
+    for (int i0 = 0; i0 < n; i0 += nth) {
+        const int cnt = std::min(nth, n - i0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < cnt; ++t)
+            th.emplace_back([&, t] { parts[t].n = 0; fmt(parts[t], i0 + t); });
+        for (auto& x : th) x.join();
+        for (int t = 0; t < cnt; ++t) fwrite(parts[t].b.data(), 1, parts[t].n, f);
     }
 }
 
@@ -592,21 +613,11 @@ int main(int argc, char** argv) {
         lb.flush();
         // 13.2 M lines per 1080p frame: CTUs are formatted by all host threads into private buffers (one CTU = 4.4 MB of
         // text each) and written in CTU order
-        const int nth = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-        std::vector<LogBuf> parts;
-        for (int t = 0; t < nth; ++t) parts.emplace_back(nullptr, 6u << 20);
         for (int poc = 0; poc < (o.allFrames ? o.nFrames : 1); ++poc) {
             const int32_t* cst = sh.keepCost[poc].data();
             const int32_t* sd = sh.keepSad[poc].empty() ? nullptr : sh.keepSad[poc].data();
             const int32_t* st = sh.keepSatd[poc].empty() ? nullptr : sh.keepSatd[poc].data();
-            for (int c0 = 0; c0 < sh.nCtus; c0 += nth) {
-                const int cnt = std::min(nth, sh.nCtus - c0);
-                std::vector<std::thread> th;
-                for (int t = 0; t < cnt; ++t)
-                    th.emplace_back([&, t] { parts[t].n = 0; write_frame_log(parts[t], poc, o.allFrames, cst, sd, st, c0 + t, c0 + t + 1, W, o.compat); });
-                for (auto& x : th) x.join();
-                for (int t = 0; t < cnt; ++t) fwrite(parts[t].b.data(), 1, parts[t].n, f);
-            }
+            format_parallel(f, sh.nCtus, 6u << 20, [&](LogBuf& b, int ctu) { write_frame_log(b, poc, o.allFrames, cst, sd, st, ctu, ctu + 1, W, o.compat); });
         }
         fclose(f);
     }
@@ -620,8 +631,8 @@ int main(int argc, char** argv) {
         for (int j = 2; j <= k; ++j) hdr += ",Mode" + std::to_string(j) + ",Cost" + std::to_string(j);
         hdr += "\n";
         lb.put(hdr.c_str(), hdr.size());
-        for (int poc = 0; poc < o.nFrames; ++poc) write_decisions(lb, poc, sh.keepMode[poc].data(), sh.keepBest[poc].data(), k, sh.nCtus, W);
         lb.flush();
+        format_parallel(f, o.nFrames, 8u << 20, [&](LogBuf& b, int poc) { write_decisions(b, poc, sh.keepMode[poc].data(), sh.keepBest[poc].data(), k, 0, sh.nCtus, W); });
         fclose(f);
     }
 
