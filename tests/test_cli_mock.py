@@ -1,0 +1,95 @@
+"""The CLI end to end WITHOUT a GPU: csrc/main.cpp linked against tests/mock_engine/mock_mipb200.cpp, a test double of the C
+ABI that answers with the CPU oracle.  What is tested here is the host plumbing of the CLI only -- options, worker threads
+and frame sharding, result handling, the text / decisions / binary log writers, the stamps -- never the CUDA engine (that is
+what the `-m gpu` tests do with the real library).  The mock is built into a temporary directory and never shipped."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from mipb200 import frames
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def mock_cli(tmp_path_factory, oracle):
+    d = tmp_path_factory.mktemp("mockcli")
+    exe = d / "mipb200_main_mock"
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-fopenmp", "-o", str(exe),
+                    os.path.join(ROOT, "vvc-mip-gpu_b200", "csrc", "main.cpp"), os.path.join(ROOT, "tests", "mock_engine", "mock_mipb200.cpp"),
+                    "-L", odir, "-lmip_oracle", f"-Wl,-rpath,{odir}"], check=True)
+
+    def run(*args, gpus=1):
+        env = dict(os.environ, MOCK_GPUS=str(gpus), OMP_NUM_THREADS="2")
+        return subprocess.run([str(exe), *args], capture_output=True, text=True, timeout=900, env=env)
+
+    return run
+
+
+def test_cost_log_of_frame_0(mock_cli, oracle, tmp_path):
+    fs = [frames.natural_frame(256, 136, 40 + i) for i in range(2)]
+    csv = tmp_path / "in.csv"
+    frames.write_csv(str(csv), fs)
+    r = mock_cli("-f", "2", "-s", "256x136", "-o", str(csv), "-l", str(tmp_path / "log"), "--UseAlternativeSamples=1",
+                 "--Filter=filterFrame_1d_float", "--KernelIdx=3")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "COMPUTING ON GPU 0" in r.stdout and "Current frame 1" in r.stdout and "TIMING RESULTS (miliseconds)" in r.stdout
+    cost, sad, satd = oracle.run_frame(fs[0], 2, 3, want_sad_satd=True)
+    lines = open(str(tmp_path / "log") + ".csv").read().splitlines()
+    assert lines[0] == "CTU,cuSizeName,W,H,CU,X,Y,Mode,SAD,SATD,minSadHad" and len(lines) - 1 == 4 * 97840
+    got = np.array([[int(v) for v in x.rsplit(",", 3)[1:]] for x in lines[1:]], dtype=np.int64).reshape(4, 97840, 3)
+    assert np.array_equal(got[..., 0], sad) and np.array_equal(got[..., 1], satd) and np.array_equal(got[..., 2], cost)
+    assert lines[1].startswith("0,ALL_AL_64x64,64,64,0,0,0,0,") and lines[1 + 3 * 97840].startswith("3,ALL_AL_64x64,64,64,0,128,128,0,")
+    for stamp in ("STARTED HOST", "START BUILD KERNELS", "FINISH BUILD KERNELS", "START WRITE SAMPLES MEMOBJ", "START ENQUEUE filterFrame",
+                  "START ENQUEUE upsamplePred_SIZEID=0", "FINISH READ DISTORTION", "FINISHED HOST"):
+        assert re.search(r"^" + re.escape(stamp) + r" @ \d\d:\d\d:\d\d\.\d\d\d$", r.stdout, re.M), stamp
+
+
+def test_all_frames_two_workers_binary_and_decision_logs(mock_cli, oracle, tmp_path):
+    """Three frames sharded over two (mock) GPUs: the POC-prefixed text log, the raw dump and the top-3 decisions log all
+    come out in POC order and equal the oracle."""
+    W, H, N = 256, 128, 3
+    fs = [frames.noise_frame(W, H, 50 + i) for i in range(N)]
+    raw = tmp_path / "in.u16"
+    np.stack(fs).astype("<u2").tofile(str(raw))
+    pre, dump, dec = tmp_path / "all", tmp_path / "c.bin", tmp_path / "dec.csv"
+    r = mock_cli("-f", str(N), "-s", f"{W}x{H}", "-o", str(raw), "--InputFormat=u16", "-l", str(pre), "--AllFrames", "--Compat", "--NumGpus=2",
+                 f"--BinaryLog={dump}", f"--DecisionsLog={dec}", "--TopK=3", gpus=2)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "COMPUTING ON GPU 0" in r.stdout and "COMPUTING ON GPU 1" in r.stdout and "on 2 GPU(s)" in r.stdout
+    want = [oracle.run_frame(f) for f in fs]
+    hdr, costs = frames.read_cost_dump(str(dump))
+    assert hdr["frames"] == N and hdr["n_ctus"] == 2 and hdr["bit_depth"] == 10
+    for poc in range(N):
+        assert np.array_equal(costs[poc], want[poc])
+    lines = open(str(pre) + ".csv").read().splitlines()
+    assert lines[0] == "POC,CTU,cuSizeName,W,H,CU,X,Y,Mode,SAD,SATD,minSadHad" and len(lines) - 1 == N * 2 * 97840
+    tail = np.array([[int(v) for v in x.rsplit(",", 3)[1:]] for x in lines[1:]], dtype=np.int64).reshape(N, 2, 97840, 3)
+    assert not tail[..., :2].any() and np.array_equal(tail[..., 2], np.stack(want))          # --Compat: SAD / SATD columns print 0
+    assert [int(x.split(",", 1)[0]) for x in lines[1::2 * 97840]] == list(range(N))
+    dl = open(dec).read().splitlines()
+    assert dl[0] == "POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost,Mode2,Cost2,Mode3,Cost3" and len(dl) - 1 == N * 2 * 5380
+    for poc in range(N):
+        tm, tc = oracle.topk(want[poc], 3)
+        rows = np.array([[int(v) for v in x.split(",")[-6:]] for x in dl[1 + poc * 10760: 1 + (poc + 1) * 10760]]).reshape(2, 5380, 3, 2)
+        assert np.array_equal(rows[..., 0], tm) and np.array_equal(rows[..., 1], tc)
+        assert dl[1 + poc * 10760].startswith(f"{poc},0,ALL_AL_64x64,64,64,0,0,0,")
+
+
+def test_device_index_out_of_range_and_bit_depth(mock_cli, oracle, tmp_path):
+    f = frames.noise_frame(128, 128, 9, bits=12)
+    raw = tmp_path / "in.u16"
+    f.astype("<u2").tofile(str(raw))
+    r = mock_cli("-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", gpus=0)
+    assert r.returncode == 0 and "Incorrect GPU index. Only 0 GPUs are detected" in r.stdout and "TIMING RESULTS" not in r.stdout
+    r = mock_cli("-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", "--NumGpus=3", gpus=2)
+    assert r.returncode == 0 and "Incorrect GPU index. Only 2 GPUs are detected" in r.stdout
+    dump = tmp_path / "c.bin"
+    r = mock_cli("-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", f"--BinaryLog={dump}", "--BitDepth=12", "--Energy")
+    assert r.returncode == 0 and "Energy counter unavailable" in r.stdout
+    hdr, costs = frames.read_cost_dump(str(dump))
+    assert hdr["bit_depth"] == 12 and np.array_equal(costs[0], oracle.run_frame(f, bit_depth=12))
