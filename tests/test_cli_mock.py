@@ -93,3 +93,34 @@ def test_device_index_out_of_range_and_bit_depth(mock_cli, oracle, tmp_path):
     assert r.returncode == 0 and "Energy counter unavailable" in r.stdout
     hdr, costs = frames.read_cost_dump(str(dump))
     assert hdr["bit_depth"] == 12 and np.array_equal(costs[0], oracle.run_frame(f, bit_depth=12))
+
+
+def test_input_formats(mock_cli, oracle, tmp_path):
+    """csv, raw u16, 8-bit yuv420p and 16-bit yuv420p10le inputs of the same two frames give the same table (chroma planes
+    are skipped; 8-bit samples are taken as they are)."""
+    W, H = 136, 72
+    f10 = [frames.natural_frame(W, H, 60 + i) for i in range(2)]
+    f8 = [(f >> 2).astype(np.uint16) for f in f10]
+    files = {}
+    p = tmp_path / "a.csv"; frames.write_csv(str(p), f10); files["csv"] = (p, f10)
+    p = tmp_path / "a.u16"; np.stack(f10).astype("<u2").tofile(str(p)); files["u16"] = (p, f10)
+    p = tmp_path / "a10.yuv"
+    with open(p, "wb") as fh:
+        for f in f10:
+            fh.write(f.astype("<u2").tobytes()); fh.write(bytes(2 * (W * H // 2)))      # Y, then U and V (16-bit, quarter size each)
+    files["yuv420p10le"] = (p, f10)
+    p = tmp_path / "a8.yuv"
+    with open(p, "wb") as fh:
+        for f in f8:
+            fh.write(f.astype(np.uint8).tobytes()); fh.write(bytes(W * H // 2))
+    files["yuv420p"] = (p, f8)
+    for fmt, (path, src) in files.items():
+        dump = tmp_path / f"{fmt}.bin"
+        r = mock_cli("-f", "2", "-s", f"{W}x{H}", "-o", str(path), f"--InputFormat={fmt}", "--NoLog", f"--BinaryLog={dump}", "--StageStamps=0")
+        assert r.returncode == 0, fmt + r.stdout + r.stderr
+        assert "START ENQUEUE" not in r.stdout
+        _, costs = frames.read_cost_dump(str(dump))
+        for poc in range(2):
+            assert np.array_equal(costs[poc], oracle.run_frame(src[poc])), (fmt, poc)
+    r = mock_cli("-f", "3", "-s", f"{W}x{H}", "-o", str(files["u16"][0]), "--InputFormat=u16", "--NoLog")
+    assert r.returncode == 1 and "holds fewer than 3 frames" in r.stderr
