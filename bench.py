@@ -13,20 +13,27 @@ hot path (filter -> MIP costs -> decisions) over a batch of B distinct frames pe
   value  frames/s with the frame pool already resident in HBM (device-timed, CUDA events)
   e2e    frames/s through the C ABI host path: host frames -> pinned ring -> H2D -> kernels -> D2H of
          the MIP decisions (best mode + its cost for every CU); e2e_costs additionally reads back the
-         full int32 cost table (the reference's minSadHad readback, 52.8 MB per 1080p frame)
-  roofline      the fused cost kernel against the binding roof: INT32 issue (algorithmic INT32 ops of
-                BASELINE.md section 2 / kernel time / measured INT32 peak); the HBM view (algorithmic
-                bytes / kernel time / measured copy bandwidth) is nested as roofline.hbm
+         full int32 cost table (the reference's minSadHad readback, 52.8 MB per 1080p frame) and is
+         repeated as e2e_like_for_like: the result the reference arm's e2e returns
+  sizes  the same three numbers for BASELINE configs 4 (3840x2160, original samples) and 5 (7680x4320,
+         alternative samples) at the current GPU count
+  shard_check   N > 1: every rank runs its poc % N share of a fixed 16-frame set, the decision hashes are
+                gathered and rank 0 compares them with its own unsharded run
+  roofline      the fused cost kernel, in the bench configuration, against the binding roof: INT32 issue
+                (algorithmic INT32 ops of BASELINE.md section 2 / kernel time / measured INT32 peak); the
+                HBM view (algorithmic bytes / kernel time / measured copy bandwidth) is nested as roofline.hbm
   cpu_baseline  the CPU oracle (port of the reference algorithm, OpenMP, all host cores) on a
                 bounded sample of the same workload (rank 0, N == 1 only)
 
 --impl reference: the reference is OpenCL-only.  The arm runs its UNMODIFIED kernels on one B200 through
-NVIDIA's OpenCL driver (oracle/_ref/mipref_ocl, built from /root/reference where it lies) and reports
-the CPU port beside it (cpu_baseline); without an OpenCL runtime it falls back to the CPU port alone.
+NVIDIA's OpenCL driver (oracle/_ref/mipref_ocl, built from /root/reference where it lies), one frame per
+step, --steps timed steps after --warmup untimed ones, and reports the CPU port beside it (cpu_baseline);
+without an OpenCL runtime it falls back to the CPU port alone.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -39,10 +46,16 @@ sys.path.insert(0, os.path.join(ROOT, "vvc-mip-gpu_b200"))
 W, H = 1920, 1080
 FILTER_NAME = "filterFrame_2d_float_5x5_quarterCtu"
 FILTER_TYPE, KERNEL_IDX = 8, 2
-N_CTUS = 135
-COSTS_PER_FRAME_IN = 12_359_520          # (CU, mode) costs of CUs inside a 1080p frame
-OPS_PER_FRAME = 1.3148e10                # algorithmic INT32 ops per 1080p frame
-ALGO_BYTES_PER_FRAME = 2 * W * H + 4 * COSTS_PER_FRAME_IN   # 53.6 MB: frame in + int32 costs out
+COSTS_PER_CTU, CUS_PER_CTU = 97840, 5380
+# the one workload string both arms print (BASELINE.json configs[1])
+WORKLOAD = f"1920x1080 10-bit natural-like synthetic frames, alternative samples {FILTER_NAME} KernelIdx={KERNEL_IDX}"
+# per frame: CTUs, in-frame (CU, mode) costs, algorithmic INT32 ops (SURVEY.md 8(d) / BASELINE.md section 2)
+GEOM = {
+    (1920, 1080): dict(n_ctus=135, costs_in=12_359_520, ops=1.3148e10),
+    (3840, 2160): dict(n_ctus=510, costs_in=49_494_960, ops=5.2766e10),
+    (7680, 4320): dict(n_ctus=2040, costs_in=198_125_280, ops=2.1155e11),
+}
+NS = 3                                      # frames in flight, like the engine's host path (3 slots)
 
 
 def _peaks():
@@ -59,6 +72,15 @@ def _int32_peak():
         d = json.load(open(p))
         return float(d["int32_tops"]), d.get("how", "profiles/int32_peak.json")
     return 148 * 128 * 1.965e-3, "nominal 148 SMs x 128 lanes x 1.965 GHz (unmeasured)"
+
+
+def _traffic():
+    """Steady-state DRAM bytes per launch of the cost kernel from the committed ncu range capture (None if absent)."""
+    for name in ("r02_cost_kernel_traffic.json", "cost_kernel_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p)).get("dram_bytes_per_launch"), "profiles/" + name
+    return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -105,9 +127,16 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def _frame_pool(n: int, seed0: int):
+def _frame_pool(n: int, seed0: int, w: int = W, h: int = H):
+    """n distinct natural-like frames.  2160p / 4320p frames are mosaics of 1080p ones (2x2 / 4x4 tiles, every tile a
+    different frame): the arithmetic of the path is data independent, so this only saves generation time."""
+    import numpy as np
     from mipb200 import frames
-    return [frames.natural_frame(W, H, seed0 + i) for i in range(n)]
+    if (w, h) == (W, H):
+        return [frames.natural_frame(W, H, seed0 + i) for i in range(n)]
+    t = w // W
+    base = [frames.natural_frame(W, H, seed0 + i) for i in range(t * t + n - 1)]
+    return [np.ascontiguousarray(np.block([[base[i + r * t + c] for c in range(t)] for r in range(t)])) for i in range(n)]
 
 
 def _cpu_port_fps(pool, seconds: float, max_frames: int):
@@ -126,7 +155,7 @@ def _cpu_port_fps(pool, seconds: float, max_frames: int):
             "sample": f"{n} frame(s) of the same workload through oracle/mip_oracle.c (OpenMP, {cores} threads)"}
 
 
-def _reference_opencl(frame, reps: int):
+def _reference_opencl(frame, reps: int, warmup: int):
     """The reference's own unmodified OpenCL kernels on this box's GPU (oracle/_ref/mipref_ocl)."""
     import subprocess
     import tempfile
@@ -137,8 +166,8 @@ def _reference_opencl(frame, reps: int):
         fp = os.path.join(d, "f.u16")
         frame.astype("<u2").tofile(fp)
         try:
-            r = subprocess.run([exe, fp, str(W), str(H), FILTER_NAME, str(KERNEL_IDX), os.path.join(d, "out"), str(reps)],
-                               capture_output=True, text=True, timeout=600)
+            r = subprocess.run([exe, fp, str(W), str(H), FILTER_NAME, str(KERNEL_IDX), os.path.join(d, "out"), str(reps), str(warmup)],
+                               capture_output=True, text=True, timeout=900)
         except subprocess.TimeoutExpired:
             return None, "mipref_ocl timed out"
     try:
@@ -154,29 +183,35 @@ def run_reference(args, rank: int, world: int) -> None:
     """Reference arm.  The reference is single-device OpenCL with no CPU implementation of its own, so the
     strongest available baseline is used: its unmodified kernels on ONE B200 through NVIDIA's OpenCL driver
     (the number BASELINE.json's ">= 50x" refers to).  Where no OpenCL runtime can be loaded the arm falls back
-    to the CPU port.  The CPU port is reported beside it either way (cpu_baseline)."""
+    to the CPU port.  The CPU port is reported beside it either way (cpu_baseline).  A step is ONE frame
+    (23 ms of kernels): --steps timed steps after --warmup untimed ones, exactly as asked."""
     if rank != 0:
         return
     pool = _frame_pool(2, 0)
-    cfg = {"workload": f"1920x1080 10-bit natural-like synthetic frames, alternative samples {FILTER_NAME} KernelIdx={KERNEL_IDX}",
-           "sample": "one frame per step"}
+    n_ctus = GEOM[(W, H)]["n_ctus"]
+    cfg = {"workload": WORKLOAD, "sample": "one frame per step (the reference host processes frames one at a time)"}
     cpu = _cpu_port_fps(pool, 10.0, 4)
-    info, why = _reference_opencl(pool[0], max(1, min(args.steps, 20)))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    info, why = _reference_opencl(pool[0], steps, warmup)
     if info is not None:
         frame_bytes = 2 * W * H
         line = {
             "impl": "reference", "metric": "1080p frames/s", "value": info["fps_kernels"], "unit": "frames/s", "n_gpus": 1,
-            "steps": info["reps"], "warmup": 1, "ms_per_step": 1e3 / info["fps_kernels"], "higher_is_better": True, "scaling": "weak",
+            "steps": info["reps"], "warmup": info.get("warmup", warmup), "ms_per_step": 1e3 / info["fps_kernels"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg,
             "reference_kind": "the reference's unmodified OpenCL kernels (intra.cl) on one %s via %s, host = oracle/ocl_ref (full grid for every frame)" % (info["device"], info["opencl_lib"]),
             "kernel_ms": {k: v for k, v in info.items() if k.startswith("ms_")},
-            "e2e": {"value": info["fps_e2e"], "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes, "d2h_bytes_per_step": 8 * N_CTUS * 97840},
+            # e2e: the stock host's behaviour -- blocking write, kernels, blocking read of the `long` table into pageable memory
+            "e2e": {"value": info["fps_e2e"], "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes, "d2h_bytes_per_step": 8 * n_ctus * COSTS_PER_CTU,
+                    "result": "the full minSadHad table as 64-bit integers (main_aux_functions.h:585-630)"},
+            # the host as it is meant to run: next upload and previous read-back overlapping the kernels (main.cpp:886-898)
+            "e2e_overlapped": {"value": info.get("fps_overlapped"), "unit": "frames/s"},
             "cpu_baseline": cpu, "gpu_launches": 0,
         }
     else:
         line = {
             "impl": "reference", "metric": "1080p frames/s", "value": cpu["value"], "unit": "frames/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": 0, "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak",
+            "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg,
             "reference_kind": "CPU port of the reference algorithm (OpenCL unavailable: %s)" % why,
             "e2e": {"value": cpu["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,14 +220,164 @@ def run_reference(args, rank: int, world: int) -> None:
     print(json.dumps(line), flush=True)
 
 
+class Workload:
+    """One (size, filter) configuration on this rank's GPU: device-resident and host-path timing."""
+
+    def __init__(self, mip, torch, np, dev_index, w, h, ft, kidx, batch, seed0, barrier):
+        self.mip, self.torch, self.np, self.dev_index = mip, torch, np, dev_index
+        self.w, self.h, self.ft, self.kidx, self.B, self.barrier = w, h, ft, kidx, batch, barrier
+        self.n_ctus = GEOM[(w, h)]["n_ctus"]
+        self.pool_np = _frame_pool(batch, seed0, w, h)
+        self.dev = torch.device("cuda", dev_index)
+        self.d_pool = torch.from_numpy(np.stack(self.pool_np).view(np.int16)).to(self.dev)          # B x H x W, resident in HBM
+        self.d_cost = torch.empty((NS, self.n_ctus, COSTS_PER_CTU), dtype=torch.int32, device=self.dev)
+        self.d_bm = torch.empty((NS, self.n_ctus, CUS_PER_CTU), dtype=torch.uint8, device=self.dev)
+        self.d_bc = torch.empty((NS, self.n_ctus, CUS_PER_CTU), dtype=torch.int32, device=self.dev)
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(NS)]   # real (non-default) streams
+
+    def engine(self, slots, emit):
+        return self.mip.Engine(self.w, self.h, device=self.dev_index, filter_type=self.ft, kernel_idx=self.kidx, slots=slots, emit=emit)
+
+    def device_resident(self, steps, warmup, sampler=None):
+        """frames already in HBM; filter -> fused MIP cost kernel (costs + decisions) per frame, frames round-robin over NS
+        streams (independent frames overlap at kernel tails exactly as in the host path).  -> (ms, launches)"""
+        torch, mip = self.torch, self.mip
+        engs = [self.engine(1, mip.EMIT_DECISIONS) for _ in range(NS)]
+
+        def step():
+            for i in range(self.B):
+                k = i % NS
+                engs[k].run_device(self.d_pool[i].data_ptr(), self.d_cost[k].data_ptr(), d_best_mode=self.d_bm[k].data_ptr(),
+                                   d_best_cost=self.d_bc[k].data_ptr(), stream=self.streams[k].cuda_stream)
+
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        if sampler:
+            sampler.start()
+        l0 = sum(e.kernel_launches() for e in engs)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(self.streams[0])
+        for s_ in self.streams[1:]:
+            s_.wait_stream(self.streams[0])
+        for _ in range(steps):
+            step()
+        for s_ in self.streams[1:]:
+            self.streams[0].wait_stream(s_)
+        ev1.record(self.streams[0])
+        self.barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = sum(e.kernel_launches() for e in engs) - l0
+        for e in engs:
+            e.close()
+        return ms, launches
+
+    def kernel_alone(self, reps):
+        """the fused kernel of THIS configuration (filter, costs + decisions) back to back on one stream -> ms per launch"""
+        torch, mip = self.torch, self.mip
+        eng = self.engine(1, mip.EMIT_DECISIONS)
+        sp = self.streams[0].cuda_stream
+
+        def go(i):
+            eng.run_device(self.d_pool[i % self.B].data_ptr(), self.d_cost[i % NS].data_ptr(), d_best_mode=self.d_bm[i % NS].data_ptr(),
+                           d_best_cost=self.d_bc[i % NS].data_ptr(), stream=sp)
+
+        for i in range(3):
+            go(i)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(self.streams[0])
+        for i in range(reps):
+            go(i)
+        k1.record(self.streams[0])
+        torch.cuda.synchronize()
+        eng.close()
+        return k0.elapsed_time(k1) / reps
+
+    def host_path(self, emit, touch_costs, steps):
+        """the application's frames live in page-locked host memory (as the contract asks): the engine DMAs them in place,
+        runs the fused kernel and copies the results back; a frame counts when collect() has returned it.  -> seconds"""
+        torch, np = self.torch, self.np
+        if not hasattr(self, "pool_host"):
+            pin = torch.empty((self.B, self.h, self.w), dtype=torch.int16, pin_memory=True)
+            pin.numpy()[...] = np.stack(self.pool_np).view(np.int16)
+            self._pin = pin
+            self.pool_host = [pin[i].numpy().view(np.uint16) for i in range(self.B)]
+        e = self.engine(NS, emit)
+
+        def step():
+            sub = got = 0
+            checksum = 0
+            while got < self.B:
+                while sub < self.B and e.in_flight() < NS:
+                    e.submit(self.pool_host[sub], poc=sub)    # async H2D from pinned memory + fused kernel + async D2H
+                    sub += 1
+                r = e.collect()                               # waits for this frame's results to be resident on the host
+                checksum += int(r.best_cost[0, 0]) + int(r.best_mode[-1, -1])
+                if touch_costs:
+                    checksum += int(r.cost[-1, -1])
+                got += 1
+            return checksum
+
+        for _ in range(2):
+            step()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e.close()
+        return dt
+
+    def free(self):
+        del self.d_pool, self.d_cost, self.d_bm, self.d_bc
+        if hasattr(self, "_pin"):
+            del self.pool_host, self._pin
+        self.torch.cuda.empty_cache()
+
+
+def _shard_check(mip, np, dist, rank, world, dev_index):
+    """Results must not depend on the number of GPUs: a fixed 16-frame set, every rank runs its poc % world share through
+    the host path and hashes the decisions; rank 0 also runs all 16 alone and compares.  With one GPU two engines stand in
+    for two ranks."""
+    from mipb200 import frames, shard
+    n = 16
+    fs = [frames.natural_frame(W, H, 9000 + i) if i % 4 else frames.noise_frame(W, H, 9000 + i) for i in range(n)]
+
+    def run(pocs):
+        out = {}
+        with mip.Engine(W, H, device=dev_index, filter_type=FILTER_TYPE, kernel_idx=KERNEL_IDX, slots=NS, emit=mip.EMIT_DECISIONS) as eng:
+            shard.run_pipelined(eng, fs, pocs, lambda poc, r: out.__setitem__(poc, hashlib.sha256(r.best_mode.tobytes() + r.best_cost.tobytes()).hexdigest()[:16]))
+        return out
+
+    if world == 1:
+        parts, how = [run(shard.frames_for_rank(n, g, 2)) for g in range(2)], "2 engines on one GPU, frames poc % 2"
+    else:
+        mine = run(shard.frames_for_rank(n, rank, world))
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        how = f"{world} ranks, frames poc % {world}, hashes all-gathered"
+    if rank != 0:
+        return None
+    whole = run(list(range(n)))
+    try:
+        merged = shard.merge_in_poc_order(parts, n)
+    except ValueError as ex:
+        return {"status": f"FAILED: {ex}", "how": how}
+    bad = [i for i in range(n) if merged[i] != whole[i]]
+    return {"status": "ok" if not bad else f"FAILED: frames {bad} differ", "frames": n, "how": how}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=32, help="1080p frames per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sizes", action="store_true", help="skip the 2160p / 4320p configurations")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -215,159 +400,103 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    B = args.batch
-    dev = torch.device("cuda", local_rank)
-    pool_np = _frame_pool(B, 1000 * rank)     # per-GPU work is fixed as N grows: weak scaling
-    emit_dec = mipb200.EMIT_DECISIONS
-    emit_full = mipb200.EMIT_COSTS | mipb200.EMIT_DECISIONS
-    NS = 3                                      # frames in flight, like the engine's host path (3 slots)
-
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident throughput (`value`) ----------------
-    # frames already in HBM; filter -> fused MIP cost kernel -> decisions per frame, frames round-robin
-    # over NS streams (independent frames overlap at kernel tails exactly as in the host path)
-    engs = [mipb200.Engine(W, H, device=local_rank, filter_type=FILTER_TYPE, kernel_idx=KERNEL_IDX, slots=1, emit=emit_dec) for _ in range(NS)]
-    d_pool = torch.from_numpy(np.stack(pool_np).view(np.int16)).to(dev)            # B x H x W, resident in HBM
-    d_cost = torch.empty((NS, N_CTUS, mipb200.COSTS_PER_CTU), dtype=torch.int32, device=dev)
-    d_bm = torch.empty((NS, N_CTUS, mipb200.CUS_PER_CTU), dtype=torch.uint8, device=dev)
-    d_bc = torch.empty((NS, N_CTUS, mipb200.CUS_PER_CTU), dtype=torch.int32, device=dev)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]   # real (non-default) streams
-    torch.cuda.synchronize()
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=torch.device("cuda", local_rank))
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
 
-    def step_device():
-        for i in range(B):
-            k = i % NS
-            engs[k].run_device(d_pool[i].data_ptr(), d_cost[k].data_ptr(), d_best_mode=d_bm[k].data_ptr(),
-                               d_best_cost=d_bc[k].data_ptr(), stream=streams[k].cuda_stream)
-
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    l0 = sum(e.kernel_launches() for e in engs)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(streams[0])
-    for s_ in streams[1:]:
-        s_.wait_stream(streams[0])
-    for _ in range(args.steps):
-        step_device()
-    for s_ in streams[1:]:
-        streams[0].wait_stream(s_)
-    ev1.record(streams[0])
-    barrier()
-    dev_ms = ev0.elapsed_time(ev1)
-    launches = sum(e.kernel_launches() for e in engs) - l0
-    clocks = sampler.stop()
-    for e in engs:
-        e.close()
-
-    # dominant kernel in isolation (roofline numerator): the fused cost kernel back to back on one stream
-    eng_k = mipb200.Engine(W, H, device=local_rank, filter_type=0, slots=1, emit=mipb200.EMIT_COSTS)
-    sp = streams[0].cuda_stream
-    for _ in range(3):
-        eng_k.run_device(d_pool[0].data_ptr(), d_cost[0].data_ptr(), stream=sp)
-    torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = max(16, min(96, args.steps * B))
-    k0.record(streams[0])
-    for i in range(reps):
-        eng_k.run_device(d_pool[i % B].data_ptr(), d_cost[i % NS].data_ptr(), stream=sp)
-    k1.record(streams[0])
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / reps
-    eng_k.close()
-
-    # ---------------- end to end through the host API (`e2e`, `e2e_costs`) ----------------
-    # the application's frames live in page-locked host memory (as the contract asks): the engine DMAs them in place
-    pool_pin = torch.empty((B, H, W), dtype=torch.int16, pin_memory=True)
-    pool_pin.numpy()[...] = np.stack(pool_np).view(np.int16)
-    pool_host = [pool_pin[i].numpy().view(np.uint16) for i in range(B)]
-
-    def step_host(e, touch_costs):
-        sub = got = 0
-        checksum = 0
-        while got < B:
-            while sub < B and e.in_flight() < NS:
-                e.submit(pool_host[sub], poc=sub)    # async H2D from pinned memory + fused kernel + async D2H
-                sub += 1
-            r = e.collect()                          # waits for this frame's results to be resident on the host
-            checksum += int(r.best_cost[0, 0]) + int(r.best_mode[-1, -1])
-            if touch_costs:
-                checksum += int(r.cost[-1, -1])
-            got += 1
-        return checksum
-
-    def time_host(emit, touch_costs):
-        e = mipb200.Engine(W, H, device=local_rank, filter_type=FILTER_TYPE, kernel_idx=KERNEL_IDX, slots=NS, emit=emit)
-        for _ in range(2):
-            step_host(e, touch_costs)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            step_host(e, touch_costs)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e.close()
-        return dt
-
+    emit_dec = mipb200.EMIT_DECISIONS
+    emit_full = mipb200.EMIT_COSTS | mipb200.EMIT_DECISIONS
+    B = args.batch
     e2e_steps = max(2, min(args.steps, 8))
-    e2e_dec_s = time_host(emit_dec, False)
-    e2e_s = time_host(emit_full, True)
 
-    # ---------------- aggregate over ranks (MAX of times) ----------------
-    times = torch.tensor([dev_ms, e2e_s * 1e3, e2e_dec_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e_dec_ms, kernel_ms = times.tolist()
-    total_frames = B * args.steps * world
-    value = total_frames / (dev_ms * 1e-3)
+    # ---------------- the headline configuration: 1080p, alternative samples ----------------
+    wl = Workload(mipb200, torch, np, local_rank, W, H, FILTER_TYPE, KERNEL_IDX, B, 1000 * rank, barrier)   # per-GPU work fixed as N grows: weak scaling
+    sampler = ClockSampler(local_rank)
+    dev_ms, launches = wl.device_resident(args.steps, args.warmup, sampler)
+    clocks = sampler.stop()
+    kernel_ms = wl.kernel_alone(max(16, min(96, args.steps * B)))
+    e2e_dec_s = wl.host_path(emit_dec, False, e2e_steps)
+    e2e_s = wl.host_path(emit_full, True, e2e_steps)
+    pool_np = wl.pool_np
+    wl.free()
+    dev_ms, e2e_ms, e2e_dec_ms, kernel_ms = max_over_ranks([dev_ms, e2e_s * 1e3, e2e_dec_s * 1e3, kernel_ms])
+    value = B * args.steps * world / (dev_ms * 1e-3)
     e2e_fps = B * e2e_steps * world / (e2e_ms * 1e-3)
     e2e_dec_fps = B * e2e_steps * world / (e2e_dec_ms * 1e-3)
 
+    # ---------------- BASELINE configs 4 and 5 at this GPU count ----------------
+    int32_peak, int32_src = _int32_peak()
+    sizes = []
+    if not args.no_sizes:
+        for name, w, h, ft, kidx, b in (("BASELINE config 4: 3840x2160 10-bit, original samples", 3840, 2160, 0, 0, 8),
+                                        (f"BASELINE config 5: 7680x4320, alternative samples {FILTER_NAME} KernelIdx={KERNEL_IDX}", 7680, 4320, FILTER_TYPE, KERNEL_IDX, 4)):
+            s_steps = max(2, min(args.steps, 6))
+            w2 = Workload(mipb200, torch, np, local_rank, w, h, ft, kidx, b, 2000 + 1000 * rank, barrier)
+            ms, _ = w2.device_resident(s_steps, 3)
+            host_s = w2.host_path(emit_dec, False, s_steps)
+            w2.free()
+            ms, host_ms = max_over_ranks([ms, host_s * 1e3])
+            g = GEOM[(w, h)]
+            fps = b * s_steps * world / (ms * 1e-3)
+            sizes.append({"workload": name, "frames_per_step_per_gpu": b, "steps": s_steps, "value": fps, "unit": "frames/s",
+                          "ms_per_frame_per_gpu": ms / (b * s_steps),
+                          "e2e": {"value": b * s_steps * world / (host_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": b * 2 * w * h,
+                                  "d2h_bytes_per_step": b * 5 * g["n_ctus"] * CUS_PER_CTU, "result": "MIP decisions"},
+                          "frac_timed_region": g["ops"] * fps / world / 1e12 / int32_peak})
+
+    shard = _shard_check(mipb200, np, dist, rank, world, local_rank)
+
     if rank == 0:
         hbm_peak, peak_src = _peaks()
-        int32_peak, int32_src = _int32_peak()
-        achieved_gbs = ALGO_BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "cost_kernel_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        g = GEOM[(W, H)]
+        algo_bytes = 2 * W * H + 4 * g["costs_in"]            # 53.6 MB: frame in + int32 costs out
+        achieved_gbs = algo_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic, traffic_src = _traffic()
         cpu = _cpu_port_fps(pool_np, 12.0, 8) if (world == 1 and not args.no_cpu_baseline) else None
         frame_bytes = 2 * W * H
-        d2h_frame = 4 * N_CTUS * mipb200.COSTS_PER_CTU + 5 * N_CTUS * mipb200.CUS_PER_CTU
+        d2h_frame = 4 * g["n_ctus"] * COSTS_PER_CTU + 5 * g["n_ctus"] * CUS_PER_CTU
+        e2e_costs = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * d2h_frame,
+                     "result": "decisions + the full int32 cost table (the reference's minSadHad readback, 52.8 MB per frame)"}
         line = {
             "metric": "1080p frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"1920x1080 10-bit natural-like synthetic frames, alternative samples {FILTER_NAME} KernelIdx={KERNEL_IDX}; "
-                                   f"batch of {B} distinct frames per GPU per step; filter + MIP costs (97840 per CTU) + decisions",
+            "config": {"workload": WORKLOAD,
+                       "batch": f"{B} distinct frames per GPU per step; filter + MIP costs (97840 per CTU) + decisions",
                        "frames_per_step_per_gpu": B, "sharding": f"frames over {world} GPU(s), no collective",
                        "l2": f"input pool {(B * frame_bytes) >> 20} MiB + 3 rotating 50 MiB cost tables exceed the 126 MiB L2 (no flush needed)"},
             "e2e": {"value": e2e_dec_fps, "unit": "frames/s", "h2d_bytes_per_step": B * frame_bytes,
-                    "d2h_bytes_per_step": B * 5 * N_CTUS * mipb200.CUS_PER_CTU,
+                    "d2h_bytes_per_step": B * 5 * g["n_ctus"] * CUS_PER_CTU,
                     "result": "MIP decisions: best_mode u8 + best_cost i32 for each of the 5380 CUs of every CTU (pinned host memory)"},
-            "e2e_costs": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * d2h_frame,
-                          "result": "decisions + the full int32 cost table (the reference's minSadHad readback, 52.8 MB per frame)"},
+            "e2e_costs": e2e_costs,
+            # full table against full table: what the reference arm's e2e returns (there as 64-bit integers)
+            "e2e_like_for_like": dict(e2e_costs, compare_with="the reference arm's e2e / e2e_overlapped (full minSadHad table on the host)"),
+            "sizes": sizes,
+            "shard_check": shard,
             "gpu_launches": launches,
             "clocks": clocks,
             # BASELINE.json's metric asks for the fraction of the SLOWER of the INT32-issue and HBM rooflines.  This path is
             # INT32-issue bound (50-90x further from the HBM roof), so `roofline` is the INT32 view and the HBM view rides
-            # inside it.  frac: the kernel alone, launches back to back on one stream (each launch pays its own ramp-up
-            # and tail); frac_timed_region: the same launches inside the timed region, where frames overlap on the slot
-            # streams (timed-region time / launches = what one launch costs the GPU in steady state).
+            # inside it.  Both are timed in the bench configuration (filter 8 / KernelIdx 2, costs + decisions).  frac: the
+            # kernel alone, launches back to back on one stream (each launch pays its own ramp-up and tail);
+            # frac_timed_region: the same launches inside the timed region, where frames overlap on the slot streams
+            # (timed-region time / launches = what one launch costs the GPU in steady state).
             "roofline": {"bound": "int32", "kernel": "mip_cost_kernel",
-                         "achieved": OPS_PER_FRAME / (kernel_ms * 1e-3) / 1e12, "peak": int32_peak, "unit": "Tops/s",
-                         "frac": OPS_PER_FRAME / (kernel_ms * 1e-3) / 1e12 / int32_peak,
-                         "frac_timed_region": OPS_PER_FRAME * value / world / 1e12 / int32_peak,
-                         "traffic": traffic, "ops_per_launch": OPS_PER_FRAME, "peak_source": int32_src,
+                         "achieved": g["ops"] / (kernel_ms * 1e-3) / 1e12, "peak": int32_peak, "unit": "Tops/s",
+                         "frac": g["ops"] / (kernel_ms * 1e-3) / 1e12 / int32_peak,
+                         "frac_timed_region": g["ops"] * value / world / 1e12 / int32_peak,
+                         "traffic": traffic, "traffic_source": traffic_src, "ops_per_launch": g["ops"], "peak_source": int32_src,
+                         "kernel_config": f"{FILTER_NAME} KernelIdx={KERNEL_IDX}, costs + decisions",
                          "kernel_ms_per_frame": kernel_ms, "ms_per_launch_timed_region": dev_ms / max(1, launches),
                          "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME, "peak_source": peak_src}},
+                                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src}},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

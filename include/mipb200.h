@@ -7,6 +7,8 @@
  * reference interface it replaces (file:line into the reference repository).
  *
  * Conventions: extern "C", plain pointers and sizes, no exceptions across the boundary.
+ * Functions that touch the GPU switch to the engine's device and restore the calling thread's current device
+ * before they return.
  * Every function returning int returns 0 on success and a negative MIPB200_E* code on
  * failure; mipb200_last_error() then holds a human-readable message (thread-local).
  * One engine drives one GPU.  An engine is not re-entrant; distinct engines may be driven
@@ -68,7 +70,8 @@ typedef struct mipb200_config {
 typedef struct mipb200_engine mipb200_engine;
 
 /* Result of one frame; pointers address the engine's pinned host ring and stay valid until
- * the next mipb200_collect()/mipb200_destroy() on the same engine.  Unrequested outputs are
+ * the next mipb200_collect()/mipb200_destroy() on the same engine -- mipb200_submit() calls in
+ * between do not touch them (the ring holds one slot more than `slots`).  Unrequested outputs are
  * NULL.  Replaces return_minSadHad/SAD/SATD (main.cpp:660, main_aux_functions.h:585-630). */
 typedef struct mipb200_result {
     int64_t poc;              /* tag given at submit */
@@ -96,8 +99,10 @@ uint16_t* mipb200_next_input(mipb200_engine* e);
 /* Enqueue one frame: async H2D from the pinned slot, filter (if any), MIP costs, decisions,
  * async D2H.  `frame` = height*width uint16 row-major, samples 0..1023 (main.cpp:364-384);
  * Pageable memory is first copied into the slot's pinned buffer; a frame that already lives in
- * page-locked memory (mipb200_next_input(), cudaHostAlloc/cudaHostRegister) is DMA'd in place and
- * must then stay untouched until the frame has been collected.  Returns immediately.
+ * page-locked memory (mipb200_next_input(), mipb200_pin_host(), cudaHostAlloc/cudaHostRegister) is DMA'd in place and
+ * must then stay alive and untouched until the frame has been collected.  Device or managed pointers are refused
+ * (MIPB200_EINVAL; see mipb200_run_device).  Samples must be < 1 << bit_depth (not checked: larger values silently
+ * overflow the packed 16-bit arithmetic -- the CLI checks its inputs).  Returns immediately.
  * Replaces one iteration of the frame loop, main.cpp:678-1241. */
 int mipb200_submit(mipb200_engine* e, const uint16_t* frame, int64_t poc);
 
@@ -143,7 +148,8 @@ long long mipb200_kernel_launches(const mipb200_engine* e);
 /* Page-lock / release a host range the caller owns (cudaHostRegister), so that mipb200_submit() DMAs frames from
  * it in place instead of staging them through the slot's pinned buffer.  The reference uploads from pageable
  * memory (clEnqueueWriteBuffer from a malloc'd array, main.cpp:580-588, 886-898).  Needs a CUDA device. */
-int mipb200_pin_host(void* ptr, size_t bytes);
+int mipb200_pin_host(void* ptr, size_t bytes);                 /* on the calling thread's current CUDA device */
+int mipb200_pin_host_on(int device, void* ptr, size_t bytes);   /* on `device` (-1 = current); the caller's current device is untouched */
 int mipb200_unpin_host(void* ptr);
 
 /* Energy counter of the board behind CUDA ordinal `device`, in millijoules since the driver was loaded (NVML,

@@ -14,11 +14,14 @@
  * runtime is dlopen()ed (NVIDIA's libnvidia-opencl.so.1 exports the whole API; the image has no
  * OpenCL headers, so the few prototypes needed are declared here -- the OpenCL 1.2 C ABI is stable).
  *
- * usage: mipref_ocl FRAME.u16 W H FILTER|none KERNELIDX OUT_PREFIX [REPS]
+ * usage: mipref_ocl FRAME.u16 W H FILTER|none KERNELIDX OUT_PREFIX [REPS [WARMUP]]
  *   reads  FRAME.u16        W*H little-endian uint16 samples
  *   writes OUT_PREFIX.cost.i32   nCTUs*97840 int32 = minSadHad of frame 0 (read back as long, narrowed)
  *          OUT_PREFIX.filt.u16   the filtered frame (when a filter is given)
- *   prints one JSON line with per-kernel device times (profiling events) and frames/s over REPS runs.
+ *   prints one JSON line with per-kernel device times (profiling events) and frames/s over REPS runs (after WARMUP
+ *   untimed ones): fps_kernels (enqueue -> clFinish, no transfers), fps_e2e (blocking write -> kernels -> blocking read,
+ *   all serial) and fps_overlapped (the reference host's intent, main.cpp:886-898 + main_aux_functions.h:617-619: the
+ *   next frame's upload and the previous frame's read-back are non-blocking and overlap the kernels).
  */
 #include <dlfcn.h>
 #include <stdint.h>
@@ -89,13 +92,14 @@ static double ev_ms(cl_event ev) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 7) { fprintf(stderr, "usage: %s FRAME.u16 W H FILTER|none KERNELIDX OUT_PREFIX [REPS]\n", argv[0]); return 1; }
+    if (argc < 7) { fprintf(stderr, "usage: %s FRAME.u16 W H FILTER|none KERNELIDX OUT_PREFIX [REPS [WARMUP]]\n", argv[0]); return 1; }
     const char* framePath = argv[1];
     const int W = atoi(argv[2]), H = atoi(argv[3]);
     const char* filter = argv[4];
     const int kernelIdx = atoi(argv[5]);
     const char* outPrefix = argv[6];
     const int reps = argc > 7 ? atoi(argv[7]) : 1;
+    const int warmup = argc > 8 ? atoi(argv[8]) : 1;
     const int useFilter = strcmp(filter, "none") != 0;
     const int ctuCols = (W + 127) / 128, ctuRows = (H + 127) / 128, nCTUs = ctuCols * ctuRows;
 
@@ -222,7 +226,7 @@ int main(int argc, char** argv) {
 
     double msFilt = 0, msInit = 0, msRed = 0, msUp[3] = {0, 0, 0};
     double tKernels = 0, tE2E = 0;
-    for (int r = 0; r < reps + 1; ++r) {   /* run 0 is a warm-up */
+    for (int r = 0; r < reps + warmup; ++r) {   /* the first `warmup` runs are not timed */
         const double tA = now_s();
         CK(p_clEnqueueWriteBuffer(q, frameBuf, CL_TRUE, 0, 2 * frameSz, frame, 0, NULL, NULL), "write frame");
         const double tB = now_s();
@@ -240,7 +244,35 @@ int main(int argc, char** argv) {
         CK(p_clEnqueueReadBuffer(q, distBuf, CL_TRUE, 0, distN * sizeof(int64_t), dist, 0, NULL, NULL), "read minSadHad");
         const double tD = now_s();
         const double f0 = useFilter ? ev_ms(ev[0]) : 0, i0 = ev_ms(ev[1]), r0 = ev_ms(ev[2]), u2 = ev_ms(ev[3]), u1 = ev_ms(ev[4]), u0 = ev_ms(ev[5]);
-        if (r > 0) { msFilt += f0; msInit += i0; msRed += r0; msUp[2] += u2; msUp[1] += u1; msUp[0] += u0; tKernels += tC - tB; tE2E += tD - tA; }
+        if (r >= warmup) { msFilt += f0; msInit += i0; msRed += r0; msUp[2] += u2; msUp[1] += u1; msUp[0] += u0; tKernels += tC - tB; tE2E += tD - tA; }
+    }
+    /* Overlapped variant: what the reference host is written to do -- upload of the next frame while the current one is
+     * computed (main.cpp:886-898) and a non-blocking read-back of the distortion (main_aux_functions.h:617-619).  The
+     * kernels keep frame-0 arguments (rep = 0), every repetition computes the same frame, so the read-back of one
+     * repetition overlapping the kernels of the next cannot change a value. */
+    double tOverlap = 0;
+    {
+        cl_command_queue qT = p_clCreateCommandQueue(ctx, dev, CL_QUEUE_PROFILING_ENABLE, &e); CK(e, "clCreateCommandQueue");
+        cl_command_queue qR = p_clCreateCommandQueue(ctx, dev, CL_QUEUE_PROFILING_ENABLE, &e); CK(e, "clCreateCommandQueue");
+        cl_mem frameNext = p_clCreateBuffer(ctx, CL_MEM_READ_WRITE, 2 * frameSz, NULL, &e); CK(e, "buf");
+        double t0 = 0;
+        for (int r = 0; r < reps + warmup; ++r) {
+            if (r == warmup) { CK(p_clFinish(qR), "finish read"); CK(p_clFinish(qT), "finish write"); t0 = now_s(); }
+            size_t g, l;
+            CK(p_clEnqueueWriteBuffer(qT, frameNext, 0 /* non-blocking */, 0, 2 * frameSz, frame, 0, NULL, NULL), "write next frame");
+            if (useFilter) { g = (size_t)4 * nCTUs * 256; l = 256; CK(p_clEnqueueNDRangeKernel(q, kFilt, 1, NULL, &g, &l, 0, NULL, NULL), "filter"); }
+            g = (size_t)47 * nCTUs * 128; l = 128; CK(p_clEnqueueNDRangeKernel(q, kInit, 1, NULL, &g, &l, 0, NULL, NULL), "initBoundaries");
+            g = (size_t)47 * nCTUs * 256; l = 256; CK(p_clEnqueueNDRangeKernel(q, kRed, 1, NULL, &g, &l, 0, NULL, NULL), "MIP_ReducedPred");
+            CK(p_clFinish(q), "finish common");
+            g = (size_t)28 * nCTUs * 256; CK(p_clEnqueueNDRangeKernel(q2, kUp[2], 1, NULL, &g, &l, 0, NULL, NULL), "upsampleDistortion id2");
+            g = (size_t)18 * nCTUs * 256; CK(p_clEnqueueNDRangeKernel(q1, kUp[1], 1, NULL, &g, &l, 0, NULL, NULL), "upsampleDistortion id1");
+            g = (size_t)8 * nCTUs * 256; CK(p_clEnqueueNDRangeKernel(q0, kUp[0], 1, NULL, &g, &l, 0, NULL, NULL), "upsampleDistortion id0");
+            CK(p_clFinish(q2), "finish id2"); CK(p_clFinish(q1), "finish id1"); CK(p_clFinish(q0), "finish id0");
+            CK(p_clFinish(qR), "previous read-back done");   /* one host array, like return_minSadHad of a frame */
+            CK(p_clEnqueueReadBuffer(qR, distBuf, 0 /* non-blocking */, 0, distN * sizeof(int64_t), dist, 0, NULL, NULL), "read minSadHad");
+        }
+        CK(p_clFinish(qR), "finish read"); CK(p_clFinish(qT), "finish write");
+        tOverlap = now_s() - t0;
     }
     /* outputs */
     {
@@ -260,8 +292,8 @@ int main(int argc, char** argv) {
     printf("{\"device\": \"%s\", \"opencl_lib\": \"%s\", \"local_mem\": %llu, \"width\": %d, \"height\": %d, \"filter\": \"%s\", \"kernel_idx\": %d, "
            "\"reps\": %d, \"build_ms\": %.1f, \"ms_filter\": %.4f, \"ms_initBoundaries\": %.4f, \"ms_MIP_ReducedPred\": %.4f, "
            "\"ms_upsampleDistortion_id2\": %.4f, \"ms_upsampleDistortion_id1\": %.4f, \"ms_upsampleDistortion_id0\": %.4f, "
-           "\"fps_kernels\": %.3f, \"fps_e2e\": %.3f}\n",
+           "\"fps_kernels\": %.3f, \"fps_e2e\": %.3f, \"fps_overlapped\": %.3f, \"warmup\": %d}\n",
            devName, used, (unsigned long long)lmem, W, H, filter, kernelIdx, reps, buildMs, msFilt / n, msInit / n, msRed / n,
-           msUp[2] / n, msUp[1] / n, msUp[0] / n, n / tKernels, n / tE2E);
+           msUp[2] / n, msUp[1] / n, msUp[0] / n, n / tKernels, n / tE2E, n / tOverlap, warmup);
     return 0;
 }

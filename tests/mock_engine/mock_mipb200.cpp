@@ -48,6 +48,7 @@ MOCK_API const char* mipb200_version(void) { return "mipb200 MOCK (tests only)";
 MOCK_API int mipb200_num_ctus(int w, int h) { return ((w + 127) / 128) * ((h + 127) / 128); }
 MOCK_API int mipb200_device_count(void) { const char* e = getenv("MOCK_GPUS"); return e ? atoi(e) : 1; }
 MOCK_API int mipb200_pin_host(void*, size_t) { return 0; }
+MOCK_API int mipb200_pin_host_on(int, void*, size_t) { return 0; }
 MOCK_API int mipb200_unpin_host(void*) { return 0; }
 MOCK_API int mipb200_device_energy_mj(int, unsigned long long*) { strcpy(g_err, "mock: no energy counter"); return MIPB200_ENODEV; }
 MOCK_API long long mipb200_kernel_launches(const mipb200_engine*) { return 0; }

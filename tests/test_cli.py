@@ -267,3 +267,56 @@ def test_log_writers_selftest(mip, tmp_path):
                     "-L", libdir, "-lmipb200", f"-Wl,-rpath,{libdir}"], check=True)
     r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "selftest: ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_streamed_ring_cycled_input_and_digest(mip, oracle, tmp_path):
+    """The streaming host on hardware: 40 frames from a 9-frame file through a 4-slot (8-slot with two GPUs) page-locked ring
+    filled by the reader thread; raw decisions at their POC offset equal the oracle; the digest repeats with the input's
+    period and does not depend on the number of GPUs."""
+    import torch
+    from mipb200 import frames
+    W, H, N, P = 384, 200, 40, 9
+    fs = [frames.natural_frame(W, H, 170 + i) if i % 2 else frames.noise_frame(W, H, 170 + i) for i in range(P)]
+    raw = tmp_path / "pool.u16"
+    np.stack(fs).astype("<u2").tofile(str(raw))
+    want = [oracle.decisions(oracle.run_frame(f, 8, 2)) for f in fs]
+    F = ["--UseAlternativeSamples=1", "--FilterType=filterFrame_2d_float_5x5_quarterCtu", "--KernelIdx=2"]
+    digests = {}
+    for g in sorted({1, min(2, torch.cuda.device_count())}):
+        dec, dig = tmp_path / f"dec{g}.bin", tmp_path / f"dig{g}.csv"
+        r = _run(mip, "-f", str(N), "-s", f"{W}x{H}", "-o", str(raw), "--InputFormat=u16", f"--InputFrames={P}", "--RingFrames=4", "--NoLog",
+                 f"--DecisionsBin={dec}", f"--Digest={dig}", f"--NumGpus={g}", "--StageStamps=0", *F)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "streamed by a reader thread" in r.stdout and "page-locked" in r.stdout
+        hdr, modes, costs = frames.read_decisions_dump(str(dec))
+        assert hdr["frames"] == N and hdr["k"] == 1 and hdr["filter_type"] == 8
+        for poc in range(N):
+            bm, bc = want[poc % P]
+            assert np.array_equal(modes[poc, :, :, 0], bm) and np.array_equal(costs[poc, :, :, 0], bc), (g, poc)
+        lines = open(dig).read().splitlines()
+        assert lines[0] == "POC,Modes,BestCosts" and len(lines) == N + 1
+        for poc in range(P, N):
+            assert lines[1 + poc].split(",")[1:] == lines[1 + poc - P].split(",")[1:]
+        digests[g] = lines
+    assert len({tuple(v) for v in digests.values()}) == 1
+    # full tables: --BinaryLog + --Digest carries a Costs column; resident ring (default capacity)
+    dump, dig = tmp_path / "c.bin", tmp_path / "digc.csv"
+    r = _run(mip, "-f", "12", "-s", f"{W}x{H}", "-o", str(raw), "--InputFormat=u16", f"--InputFrames={P}", "--NoLog", f"--BinaryLog={dump}", f"--Digest={dig}", "--StageStamps=0", *F)
+    assert r.returncode == 0 and "resident" in r.stdout, r.stdout + r.stderr
+    _, costs = frames.read_cost_dump(str(dump))
+    for poc in (0, 5, 11):
+        assert np.array_equal(costs[poc], oracle.run_frame(fs[poc % P], 8, 2)), poc
+    lines = open(dig).read().splitlines()
+    assert lines[0] == "POC,Costs,Modes,BestCosts" and lines[1].split(",")[1:] == lines[10].split(",")[1:]
+    assert lines[1].split(",")[2:] == digests[1][1].split(",")[1:]          # same decisions hash as the decisions-only run
+
+
+@pytest.mark.gpu
+def test_cli_rejects_samples_beyond_the_bit_depth(mip, tmp_path):
+    from mipb200 import frames
+    f = frames.noise_frame(128, 128, 3, bits=12)
+    raw = tmp_path / "in.u16"
+    f.astype("<u2").tofile(str(raw))
+    r = _run(mip, "-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog")
+    assert r.returncode == 1 and "does not fit 10 bits" in r.stderr

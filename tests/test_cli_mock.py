@@ -84,9 +84,9 @@ def test_device_index_out_of_range_and_bit_depth(mock_cli, oracle, tmp_path):
     f = frames.noise_frame(128, 128, 9, bits=12)
     raw = tmp_path / "in.u16"
     f.astype("<u2").tofile(str(raw))
-    r = mock_cli("-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", gpus=0)
+    r = mock_cli("-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", "--BitDepth=12", gpus=0)
     assert r.returncode == 0 and "Incorrect GPU index. Only 0 GPUs are detected" in r.stdout and "TIMING RESULTS" not in r.stdout
-    r = mock_cli("-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", "--NumGpus=3", gpus=2)
+    r = mock_cli("-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", "--BitDepth=12", "--NumGpus=3", gpus=2)
     assert r.returncode == 0 and "Incorrect GPU index. Only 2 GPUs are detected" in r.stdout
     dump = tmp_path / "c.bin"
     r = mock_cli("-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", f"--BinaryLog={dump}", "--BitDepth=12", "--Energy")
@@ -124,3 +124,87 @@ def test_input_formats(mock_cli, oracle, tmp_path):
             assert np.array_equal(costs[poc], oracle.run_frame(src[poc])), (fmt, poc)
     r = mock_cli("-f", "3", "-s", f"{W}x{H}", "-o", str(files["u16"][0]), "--InputFormat=u16", "--NoLog")
     assert r.returncode == 1 and "holds fewer than 3 frames" in r.stderr
+
+
+def test_samples_must_fit_the_bit_depth(mock_cli, tmp_path):
+    """A sample >= 1 << BitDepth would overflow the engine's packed 16-bit arithmetic silently: the readers refuse it and say where it is."""
+    f = frames.noise_frame(128, 128, 9, bits=10)
+    f[5, 77] = 1024
+    raw = tmp_path / "in.u16"
+    f.astype("<u2").tofile(str(raw))
+    r = mock_cli("-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog")
+    assert r.returncode == 1 and "sample 1024 at row 5, column 77 does not fit 10 bits" in r.stderr
+    csv = tmp_path / "in.csv"
+    frames.write_csv(str(csv), [f])
+    r = mock_cli("-f", "1", "-s", "128x128", "-o", str(csv), "--NoLog")
+    assert r.returncode == 1 and "sample 1024 at row 5, column 77 does not fit 10 bits" in r.stderr
+    r = mock_cli("-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", "--BitDepth=12")
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_streamed_ring_cycled_input_binary_decisions_and_digest(mock_cli, oracle, tmp_path):
+    """Twenty frames from a nine-frame file (--InputFrames 9) through a four- or eight-slot ring: the reader thread streams and rewinds,
+    two workers shard the frames, decisions land raw at their POC offset, and the digest is the same for one and two workers
+    and repeats with the input's period."""
+    W, H, N, P = 136, 72, 20, 9
+    fs = [frames.natural_frame(W, H, 70 + i) for i in range(P)]
+    raw = tmp_path / "pool.u16"
+    np.stack(fs).astype("<u2").tofile(str(raw))
+    want = [oracle.decisions(oracle.run_frame(f, 3, 1)) for f in fs]
+    digests = {}
+    for g in (1, 2):
+        dec, dig = tmp_path / f"dec{g}.bin", tmp_path / f"dig{g}.csv"
+        r = mock_cli("-f", str(N), "-s", f"{W}x{H}", "-o", str(raw), "--InputFormat=u16", f"--InputFrames={P}", "--RingFrames=4", "--NoLog",
+                     f"--DecisionsBin={dec}", f"--Digest={dig}", f"--NumGpus={g}", "--UseAlternativeSamples=1",
+                     "--FilterType=filterFrame_2d_int_quarterCtu", "--KernelIdx=1", gpus=2)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "streamed by a reader thread" in r.stdout and f"Frame ring: {4 * g} x" in r.stdout
+        hdr, modes, costs = frames.read_decisions_dump(str(dec))
+        assert hdr == dict(version=1, width=W, height=H, frames=N, n_ctus=2, cus_per_ctu=5380, bit_depth=10, filter_type=3, kernel_idx=1, k=1)
+        for poc in range(N):
+            bm, bc = want[poc % P]
+            assert np.array_equal(modes[poc, :, :, 0], bm) and np.array_equal(costs[poc, :, :, 0], bc), (g, poc)
+        lines = open(dig).read().splitlines()
+        assert lines[0] == "POC,Modes,BestCosts" and [ln.split(",")[0] for ln in lines[1:]] == [str(i) for i in range(N)]
+        digests[g] = lines
+        for poc in range(P, N):
+            assert lines[1 + poc].split(",")[1:] == lines[1 + poc - P].split(",")[1:]
+        assert len({ln.split(",", 1)[1] for ln in lines[1:1 + P]}) == P          # distinct frames hash differently
+    assert digests[1] == digests[2]
+    # a resident ring (the default: the nine distinct frames fit) gives the same bytes
+    dec = tmp_path / "dec_res.bin"
+    r = mock_cli("-f", str(N), "-s", f"{W}x{H}", "-o", str(raw), "--InputFormat=u16", f"--InputFrames={P}", "--NoLog", f"--DecisionsBin={dec}",
+                 "--UseAlternativeSamples=1", "--FilterType=filterFrame_2d_int_quarterCtu", "--KernelIdx=1")
+    assert r.returncode == 0 and "resident" in r.stdout
+    assert open(dec, "rb").read() == open(tmp_path / "dec1.bin", "rb").read()
+
+
+def test_streamed_csv_input_and_all_frames_logs(mock_cli, oracle, tmp_path):
+    """A CSV larger than the ring is parsed incrementally; the POC-ordered text logs of a streamed, two-worker run equal the oracle."""
+    W, H, N = 136, 72, 5
+    fs = [frames.noise_frame(W, H, 90 + i) for i in range(N)]
+    csv = tmp_path / "in.csv"
+    frames.write_csv(str(csv), fs)
+    pre, dec = tmp_path / "all", tmp_path / "dec.csv"
+    r = mock_cli("-f", str(N), "-s", f"{W}x{H}", "-o", str(csv), "--RingFrames=2", "--NumGpus=2", "-l", str(pre), "--AllFrames", "--Compat",
+                 f"--DecisionsLog={dec}", gpus=2)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Frame ring: 5 x" in r.stdout and "resident" in r.stdout          # at least four frames per GPU: all five fit
+    r = mock_cli("-f", str(N), "-s", f"{W}x{H}", "-o", str(csv), "--RingFrames=2", "-l", str(pre), "--AllFrames", "--Compat", f"--DecisionsLog={dec}")
+    assert r.returncode == 0 and "Frame ring: 4 x" in r.stdout and "streamed" in r.stdout
+    want = [oracle.run_frame(f) for f in fs]
+    lines = open(str(pre) + ".csv").read().splitlines()
+    assert len(lines) - 1 == N * 2 * 97840
+    got = np.array([int(x[x.rfind(",") + 1:]) for x in lines[1:]], dtype=np.int32).reshape(N, 2, 97840)
+    assert np.array_equal(got, np.stack(want))
+    assert [int(x.split(",", 1)[0]) for x in lines[1::2 * 97840]] == list(range(N))
+    dl = open(dec).read().splitlines()
+    assert len(dl) - 1 == N * 2 * 5380
+    for poc in range(N):
+        bm, bc = oracle.decisions(want[poc])
+        rows = dl[1 + poc * 10760: 1 + (poc + 1) * 10760]
+        assert np.array_equal(np.array([int(x.split(",")[-2]) for x in rows]).reshape(2, 5380), bm)
+        assert np.array_equal(np.array([int(x.split(",")[-1]) for x in rows]).reshape(2, 5380), bc)
+    # a short CSV is still an error, reported with the line count
+    r = mock_cli("-f", str(N + 1), "-s", f"{W}x{H}", "-o", str(csv), "--RingFrames=2", "--NoLog")
+    assert r.returncode == 1 and f"holds {N * H} lines, need {(N + 1) * H}" in r.stderr

@@ -10,14 +10,24 @@
 // README's --Filter=... works; values may follow as "--Opt=value" or "--Opt value".
 // USE_ALTERNATIVE_SAMPLES is the reference's compile-time switch (main.cpp:10); here it is the
 // default of the run-time option --UseAlternativeSamples (0|1).
-// Extensions (all off by default): --NumGpus G (frames sharded poc % G over G GPUs, one host
-// thread each, no collective), --AllFrames (log every frame with a leading POC column),
-// --Compat (print 0 in the SAD/SATD columns like the reference's MAX_PERFORMANCE_DIST build),
-// --NoLog (skip the text log), --InputFormat csv|u16|yuv420p|yuv420p10le (binary luma input instead of
-// the 2 M stoi() calls per 1080p frame), --DecisionsLog FILE (per-CU best mode + cost of EVERY frame,
-// keyed by POC,X,Y,W,H: the table an encoder-side consumer ingests), --TopK k (shortlists in that log),
-// --BinaryLog FILE (raw int32 cost tables of every frame), --BitDepth 8|10|12, --Energy (NVML joules per frame),
-// --StageStamps 0|1 (the reference's TRACE_POWER stamps).
+//
+// Memory model.  The reference reads every frame into one array and keeps every frame's table (main.cpp:364-384,
+// :656-662); that is 250 GB for BASELINE config 5 (2048 frames of 7680x4320).  Here frames live in a bounded,
+// page-locked RING (--RingFrames, default: 2 GiB worth, at least 4 per GPU) that the engines DMA from in place.  When
+// the input fits the ring it is loaded before the timed window, exactly like the reference; otherwise a reader thread
+// streams it (the ring is full when the window opens, slots are refilled as their frames are collected).  Results are
+// consumed frame by frame as they are collected -- written to their place in the binary logs (pwrite), hashed into the
+// digest, or formatted and appended in POC order to the text logs -- so host memory does not grow with -f.
+//
+// Extensions (all off by default): --NumGpus G (frames sharded poc % G over G GPUs, one host thread each, no
+// collective), --AllFrames (log every frame with a leading POC column), --Compat (print 0 in the SAD/SATD columns like
+// the reference's MAX_PERFORMANCE_DIST build), --NoLog (skip the text log), --InputFormat csv|u16|yuv420p|yuv420p10le
+// (binary luma input instead of the 2 M stoi() calls per 1080p frame), --InputFrames P (the file holds P frames, frame
+// poc is file frame poc % P: a pool cycled like SURVEY 8(d) configs 4/5), --DecisionsLog FILE (text: per-CU best mode
+// + cost of EVERY frame keyed by POC,X,Y,W,H), --DecisionsBin FILE (the same table raw: 5 bytes per CU), --TopK k
+// (shortlists in both), --BinaryLog FILE (raw int32 cost tables of every frame), --Digest FILE (one 64-bit hash per
+// frame and result array: what G-independence is checked with), --BitDepth 8|10|12, --Energy (NVML joules per
+// frame), --StageStamps 0|1 (the reference's TRACE_POWER stamps).
 //
 // The device work goes through the C ABI of include/mipb200.h only.
 #include <errno.h>
@@ -26,12 +36,15 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/resource.h>
 #include <sys/time.h>
 #include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -61,15 +74,18 @@ struct Options {
     int topK = 0;
     int bitDepth = 10;
     int stageStamps = -1;   // -1: follow TRACE_POWER when one GPU is used
-    std::string inputFormat = "csv", decisionsLog, binaryLog;
+    int inputFrames = 0;    // frames the input file holds (0: as many as -f); frame poc is file frame poc % inputFrames
+    int ringFrames = 0;     // capacity of the page-locked frame ring (0: 2 GiB worth, at least 4 per GPU)
+    std::string inputFormat = "csv", decisionsLog, binaryLog, decisionsBin, digest;
     bool allFrames = false, compat = false, noLog = false, help = false, energy = false;
 };
 
 const char* kLongOpts[] = {"help", "DeviceIndex", "FramesToBeEncoded", "Resolution", "OriginalFrames", "OutputPreffix",
                            "FilterType", "KernelIdx", "UseAlternativeSamples", "NumGpus", "AllFrames", "Compat", "NoLog",
-                           "InputFormat", "DecisionsLog", "TopK", "Energy", "StageStamps", "BitDepth", "BinaryLog"};
+                           "InputFormat", "DecisionsLog", "TopK", "Energy", "StageStamps", "BitDepth", "BinaryLog", "DecisionsBin", "Digest",
+                           "InputFrames", "RingFrames"};
 const bool kTakesValue[] = {false, true, true, true, true, true, true, true, true, true, false, false, false, true, true,
-                            true, false, true, true, true};
+                            true, false, true, true, true, true, true, true, true};
 constexpr int kNumOpts = sizeof(kLongOpts) / sizeof(kLongOpts[0]);
 
 void print_help() {
@@ -88,6 +104,10 @@ void print_help() {
            "  --InputFormat arg (=csv)       csv | u16 (raw little-endian luma) | yuv420p | yuv420p10le\n"
            "  --DecisionsLog arg             write POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost for every frame\n"
            "  --BinaryLog arg                write every frame's cost table as raw int32 (64-byte header, see INTEGRATION.md)\n"
+           "  --DecisionsBin arg             write every frame's decisions raw: uint8 modes then int32 costs (64-byte header)\n"
+           "  --Digest arg                   write POC,<64-bit hash of each result array> for every frame\n"
+           "  --InputFrames arg              frames held by the input file; frame poc reads file frame poc %% arg (default: -f)\n"
+           "  --RingFrames arg               capacity of the page-locked frame ring (default: 2 GiB worth, >= 4 per GPU)\n"
            "  --TopK arg (=1)                with --DecisionsLog: the k cheapest modes per CU (adds Mode2,Cost2,... columns)\n"
            "  --Energy                       report joules per frame from the board's NVML energy counter\n"
            "  --BitDepth arg (=10)           8 | 10 | 12; 10 is the reference's pipeline (also for 8-bit content taken as is)\n"
@@ -169,6 +189,10 @@ bool parse_args(int argc, char** argv, Options& o) {
             case 17: ok = to_int(val, &o.stageStamps); break;
             case 18: ok = to_int(val, &o.bitDepth); break;
             case 19: o.binaryLog = val; break;
+            case 20: o.decisionsBin = val; break;
+            case 21: o.digest = val; break;
+            case 22: ok = to_int(val, &o.inputFrames); break;
+            case 23: ok = to_int(val, &o.ringFrames); break;
         }
         if (!ok) { fprintf(stderr, "the argument ('%s') for option '--%s' is invalid\n", val.c_str(), kLongOpts[opt]); return false; }
     }
@@ -210,64 +234,154 @@ double now_ms() {
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-// CSV reader (main.cpp:364-384): N*H lines of W comma-separated integers; extra fields ignored.
-bool read_frames_csv(const std::string& path, int W, int H, int N, std::vector<uint16_t>& out) {
-    FILE* f = fopen(path.c_str(), "rb");
-    if (!f) { perror("error while opening samples files"); return false; }
-    fseek(f, 0, SEEK_END);
-    long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    std::vector<char> buf((size_t)sz + 1);
-    if (fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); fprintf(stderr, "short read on %s\n", path.c_str()); return false; }
-    fclose(f);
-    buf[sz] = '\n';
-    out.resize((size_t)W * H * N);
-    const char* p = buf.data();
-    const char* end = p + sz;
-    for (long line = 0; line < (long)N * H; ++line) {
-        if (p >= end) { fprintf(stderr, "[!] ERROR: %s holds %ld lines, need %ld (%d frames of %d rows)\n", path.c_str(), line, (long)N * H, N, H); return false; }
-        uint16_t* dst = out.data() + (size_t)line * W;
-        for (int x = 0; x < W; ++x) {
-            while (p < end && (*p == ' ' || *p == '\t')) ++p;
-            if (p >= end || *p < '0' || *p > '9') {
-                fprintf(stderr, "[!] ERROR: line %ld of %s: field %d is not a number (need %d samples per line)\n", line + 1, path.c_str(), x + 1, W);
+// Sequential reader of luma frames, one frame per call (nothing but the current frame is held):
+//   csv          N*H lines of W comma-separated integers, extra fields ignored (main.cpp:364-384)
+//   u16          W*H little-endian uint16 per frame
+//   yuv420p      8-bit planar 4:2:0, chroma skipped        yuv420p10le  16-bit planar 4:2:0, chroma skipped
+// Sample values are taken as they are (the pipeline is 10-bit by default, intra.cl:61) but must fit --BitDepth: larger
+// values would overflow the engine's packed 16-bit arithmetic silently, so they are an input error here.
+class FrameSource {
+  public:
+    ~FrameSource() { if (f_) fclose(f_); }
+    bool open(const std::string& path, const std::string& fmt, int W, int H, int bitDepth, long framesWanted) {
+        path_ = path; fmt_ = fmt; W_ = W; H_ = H; bits_ = bitDepth; wanted_ = framesWanted;
+        f_ = fopen(path.c_str(), "rb");
+        if (!f_) { perror("error while opening samples files"); return false; }
+        if (fmt == "csv") buf_.resize(4u << 20);
+        else if (fmt == "yuv420p") tmp_.resize((size_t)W * H);
+        return true;
+    }
+    void rewind_to_start() { fseek(f_, 0, SEEK_SET); beg_ = end_ = 0; line_ = 0; frame_ = 0; }
+    // next frame of the file into dst[H][W]; false (message on stderr) on a short file, a malformed field or an out-of-range sample
+    bool next(uint16_t* dst) {
+        const bool ok = fmt_ == "csv" ? next_csv(dst) : next_binary(dst);
+        if (!ok) return false;
+        unsigned all = 0;
+        const size_t px = (size_t)W_ * H_;
+        for (size_t i = 0; i < px; ++i) all |= dst[i];
+        if (all >> bits_) {
+            size_t i = 0;
+            while (!(dst[i] >> bits_)) ++i;
+            fprintf(stderr, "[!] ERROR: frame %ld of %s: sample %u at row %zu, column %zu does not fit %d bits (see --BitDepth)\n", frame_, path_.c_str(),
+                    (unsigned)dst[i], i / W_, i % W_, bits_);
+            return false;
+        }
+        ++frame_;
+        return true;
+    }
+
+  private:
+    int getc_buf() {
+        if (beg_ == end_) {
+            end_ = fread(buf_.data(), 1, buf_.size(), f_);
+            beg_ = 0;
+            if (end_ == 0) return -1;
+        }
+        return (unsigned char)buf_[beg_++];
+    }
+    bool next_csv(uint16_t* dst) {
+        for (int y = 0; y < H_; ++y, ++line_) {
+            int c = getc_buf();
+            if (c < 0) {
+                fprintf(stderr, "[!] ERROR: %s holds %ld lines, need %ld (%ld frames of %d rows)\n", path_.c_str(), line_, wanted_ * H_, wanted_, H_);
                 return false;
             }
-            int v = 0;
-            while (*p >= '0' && *p <= '9') v = v * 10 + (*p++ - '0');
-            dst[x] = (uint16_t)v;
-            if (*p == ',') ++p;
+            uint16_t* row = dst + (size_t)y * W_;
+            for (int x = 0; x < W_; ++x) {
+                while (c == ' ' || c == '\t') c = getc_buf();
+                if (c < '0' || c > '9') {
+                    fprintf(stderr, "[!] ERROR: line %ld of %s: field %d is not a number (need %d samples per line)\n", line_ + 1, path_.c_str(), x + 1, W_);
+                    return false;
+                }
+                unsigned v = 0;
+                while (c >= '0' && c <= '9') { v = v * 10 + (unsigned)(c - '0'); if (v > 65535u) v = 65535u; c = getc_buf(); }
+                row[x] = (uint16_t)v;
+                if (c == ',') c = getc_buf();
+            }
+            while (c >= 0 && c != '\n') c = getc_buf();
         }
-        while (p < end && *p != '\n') ++p;
-        ++p;
+        return true;
     }
-    return true;
-}
-
-// Binary luma input: u16 = W*H little-endian uint16 per frame; yuv420p = 8-bit planar 4:2:0 (chroma skipped);
-// yuv420p10le = 16-bit planar 4:2:0.  Sample values are taken as they are (the pipeline is 10-bit, intra.cl:61).
-bool read_frames_binary(const std::string& path, const std::string& fmt, int W, int H, int N, std::vector<uint16_t>& out) {
-    FILE* f = fopen(path.c_str(), "rb");
-    if (!f) { perror("error while opening samples files"); return false; }
-    const size_t px = (size_t)W * H;
-    out.resize(px * N);
-    const bool eight = fmt == "yuv420p";
-    const size_t chroma = fmt == "u16" ? 0 : px / 2 * (eight ? 1 : 2);
-    std::vector<uint8_t> tmp(eight ? px : 0);
-    for (int n = 0; n < N; ++n) {
-        uint16_t* dst = out.data() + px * n;
+    bool next_binary(uint16_t* dst) {
+        const size_t px = (size_t)W_ * H_;
+        const bool eight = fmt_ == "yuv420p";
+        const size_t chroma = fmt_ == "u16" ? 0 : px / 2 * (eight ? 1 : 2);
         size_t got;
         if (eight) {
-            got = fread(tmp.data(), 1, px, f);
-            for (size_t i = 0; i < px; ++i) dst[i] = tmp[i];
+            got = fread(tmp_.data(), 1, px, f_);
+            for (size_t i = 0; i < px; ++i) dst[i] = tmp_[i];
         } else {
-            got = fread(dst, 2, px, f);
+            got = fread(dst, 2, px, f_);
         }
-        if (got != px) { fprintf(stderr, "[!] ERROR: %s holds fewer than %d frames of %dx%d (%s)\n", path.c_str(), N, W, H, fmt.c_str()); fclose(f); return false; }
-        if (chroma && fseek(f, (long)chroma, SEEK_CUR) != 0) { fclose(f); return false; }
+        if (got != px) {
+            fprintf(stderr, "[!] ERROR: %s holds fewer than %ld frames of %dx%d (%s)\n", path_.c_str(), wanted_, W_, H_, fmt_.c_str());
+            return false;
+        }
+        return !chroma || fseek(f_, (long)chroma, SEEK_CUR) == 0;
     }
-    fclose(f);
-    return true;
+    FILE* f_ = nullptr;
+    std::string path_, fmt_;
+    int W_ = 0, H_ = 0, bits_ = 10;
+    long wanted_ = 0, line_ = 0, frame_ = 0;
+    std::vector<char> buf_;
+    size_t beg_ = 0, end_ = 0;
+    std::vector<uint8_t> tmp_;
+};
+
+// Page-locked ring the engines DMA frames from in place.  `period` = distinct frames (-f, or --InputFrames when smaller).
+//  * resident (period <= capacity): slot = poc % period, filled once before the timed window, never released;
+//  * streamed: slot = poc % capacity; the reader thread fills frames in POC order as slots are released by the worker
+//    that collected their frame.  Capacity >= 4 frames per GPU keeps the reader ahead of 3 frames in flight per engine.
+struct FrameRing {
+    int capacity = 0, period = 0;
+    bool resident = true;
+    size_t fpx = 0;
+    uint16_t* base = nullptr;
+    bool pinned = false;
+    std::vector<long> holds;      // POC whose samples the slot holds (-1: none yet)
+    std::vector<char> busy;       // streamed mode: filled and not yet released
+    long filled = 0;              // frames read so far
+    bool failed = false;
+    std::mutex mu;
+    std::condition_variable cv;
+
+    int slot_of(long poc) const { return (int)(resident ? poc % period : poc % capacity); }
+    uint16_t* slot_ptr(int s) const { return base + fpx * (size_t)s; }
+    // worker: wait until frame poc is in the ring; nullptr if the reader failed
+    const uint16_t* acquire(long poc) {
+        const int s = slot_of(poc);
+        if (resident) return slot_ptr(s);
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return failed || (holds[s] == poc && busy[s]); });
+        return failed ? nullptr : slot_ptr(s);
+    }
+    void release(long poc) {
+        if (resident) return;
+        std::lock_guard<std::mutex> lk(mu);
+        busy[slot_of(poc)] = 0;
+        cv.notify_all();
+    }
+    void fail() { std::lock_guard<std::mutex> lk(mu); failed = true; cv.notify_all(); }
+};
+
+// 64-bit digest of a result array (4 interleaved multiply-rotate lanes over 64-bit words, then a fold): fast enough to
+// run inside the collect loop (several GB/s per host thread) and sensitive to any changed, moved or missing word.
+uint64_t digest64(const void* data, size_t bytes) {
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    uint64_t h[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
+    const uint64_t m0 = 0xFF51AFD7ED558CCDull, m1 = 0xC4CEB9FE1A85EC53ull;
+    size_t n = bytes / 32;
+    for (size_t i = 0; i < n; ++i, p += 32) {
+        uint64_t w[4];
+        memcpy(w, p, 32);
+        for (int k = 0; k < 4; ++k) { h[k] = (h[k] ^ w[k]) * m0; h[k] = (h[k] << 29) | (h[k] >> 35); }
+    }
+    uint64_t tail[4] = {0, 0, 0, 0};
+    memcpy(tail, p, bytes % 32);
+    for (int k = 0; k < 4; ++k) { h[k] = (h[k] ^ tail[k]) * m0; h[k] = (h[k] << 29) | (h[k] >> 35); }
+    uint64_t r = bytes;
+    for (int k = 0; k < 4; ++k) { r = (r ^ h[k]) * m1; r ^= r >> 32; }
+    return r;
 }
 
 // ---- cost log (main_aux_functions.h:735-798)
@@ -367,19 +481,50 @@ void format_parallel(FILE* f, int n, size_t bufBytes, Fmt fmt) {
     }
 }
 
+// A text log that frames reach out of order (one worker per GPU) but that must be written in POC order: a worker waits
+// for its frame's turn, formats and writes (in bounded rounds, all host threads formatting), and passes the turn on.
+// Workers take their frames in increasing POC order and the frame ring holds more frames than can be in flight, so the
+// smallest outstanding POC can always proceed: no deadlock.
+struct OrderedLog {
+    FILE* f = nullptr;
+    long next = 0;
+    bool failed = false;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool begin(long poc) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return failed || next == poc; });
+        return !failed;
+    }
+    void end() { std::lock_guard<std::mutex> lk(mu); ++next; cv.notify_all(); }
+    void abort() { std::lock_guard<std::mutex> lk(mu); failed = true; cv.notify_all(); }
+};
+
 struct Shared {
     Options opt;
-    int W = 0, H = 0, nCtus = 0, filterType = 0;
-    const uint16_t* frames = nullptr;
-    std::vector<std::vector<int32_t>> keepCost, keepSad, keepSatd;  // per frame, only those that get logged
-    std::vector<std::vector<uint8_t>> keepMode;                     // per frame, with --DecisionsLog
-    std::vector<std::vector<int32_t>> keepBest;
+    int W = 0, H = 0, nCtus = 0, filterType = 0, k = 1;             // k: entries per CU in the decision arrays (--TopK)
+    unsigned emit = 0;                                              // MIPB200_EMIT_* of every engine
+    FrameRing ring;
+    std::vector<int32_t> keepCost, keepSad, keepSatd;               // frame 0 only: the reference's log (main.cpp:1268)
+    std::vector<uint64_t> digCost, digMode, digBest;                // --Digest: one hash per frame and array
     std::atomic<int> errors{0};
     bool stamps = false;
-    int binFd = -1;                                                 // --BinaryLog
+    int binFd = -1, decFd = -1;                                     // --BinaryLog, --DecisionsBin
+    OrderedLog costLog, decLog;                                     // --AllFrames text log, --DecisionsLog
 };
 
 constexpr int kBinHeader = 64;   // "MIPB200C", then u32 version, width, height, frames, CTUs, costs per CTU, bit depth, filter type, kernel index
+                                 // "MIPB200D", then u32 version, width, height, frames, CTUs, CUs per CTU, bit depth, filter type, kernel index, k
+
+bool pwrite_all(int fd, const void* data, size_t bytes, off_t off) {
+    const char* src = static_cast<const char*>(data);
+    while (bytes) {
+        const ssize_t w = pwrite(fd, src, bytes, off);
+        if (w <= 0) return false;
+        src += w; off += w; bytes -= (size_t)w;
+    }
+    return true;
+}
 
 // Engine of GPU g: context, streams, pinned rings, tables.  Runs before the timed window, like the reference's
 // platform / queue / buffer / program setup (main.cpp:87-549).
@@ -390,9 +535,7 @@ mipb200_engine* create_engine(Shared* sh, int g, mipb200_config* cfg_out) {
     cfg.filter_type = sh->filterType; cfg.kernel_idx = o.kernelIdx; cfg.slots = 3;
     cfg.top_k = o.topK > 1 ? o.topK : 0;
     cfg.bit_depth = o.bitDepth;
-    const bool wantLog = !o.noLog, wantDec = !o.decisionsLog.empty(), wantBin = !o.binaryLog.empty();
-    cfg.emit = (wantLog || wantBin || !wantDec ? MIPB200_EMIT_COSTS : 0) | (wantLog && !o.compat ? MIPB200_EMIT_SAD_SATD : 0) |
-               (wantDec ? MIPB200_EMIT_DECISIONS : 0);
+    cfg.emit = sh->emit;
     mipb200_engine* e = nullptr;
     if (mipb200_create(&e, &cfg) != 0) {
         fprintf(stderr, "[!] ERROR (GPU %d): %s\n", cfg.device, mipb200_last_error());
@@ -403,43 +546,62 @@ mipb200_engine* create_engine(Shared* sh, int g, mipb200_config* cfg_out) {
     return e;
 }
 
+// What happens to a frame's results, on the worker thread that collected them, while the GPU works on the next frames.
+bool consume_result(Shared* sh, const mipb200_result& r) {
+    const Options& o = sh->opt;
+    const long poc = (long)r.poc;
+    const size_t ncost = (size_t)sh->nCtus * MIP_COSTS_PER_CTU, ncu = (size_t)sh->nCtus * MIP_CUS_PER_CTU * sh->k;
+    const uint8_t* bm = r.top_k ? r.topk_mode : r.best_mode;
+    const int32_t* bc = r.top_k ? r.topk_cost : r.best_cost;
+    if (sh->binFd >= 0 && !pwrite_all(sh->binFd, r.cost, ncost * sizeof(int32_t), (off_t)kBinHeader + (off_t)poc * (off_t)(ncost * sizeof(int32_t)))) {
+        perror("error while writing the binary log");   // raw table straight from the pinned ring to its place in the file
+        return false;
+    }
+    if (sh->decFd >= 0) {   // frame record: modes [nCTU][5380][k] uint8, then costs [nCTU][5380][k] int32
+        const off_t rec = (off_t)(ncu * 5), off = (off_t)kBinHeader + (off_t)poc * rec;
+        if (!pwrite_all(sh->decFd, bm, ncu, off) || !pwrite_all(sh->decFd, bc, ncu * sizeof(int32_t), off + (off_t)ncu)) {
+            perror("error while writing the binary decisions");
+            return false;
+        }
+    }
+    if (!o.digest.empty()) {
+        if (r.cost) sh->digCost[poc] = digest64(r.cost, ncost * sizeof(int32_t));
+        if (bm) { sh->digMode[poc] = digest64(bm, ncu); sh->digBest[poc] = digest64(bc, ncu * sizeof(int32_t)); }
+    }
+    if (!o.noLog && !o.allFrames && poc == 0) {   // the reference exports frame 0 only (main.cpp:1268), after the timed window
+        memcpy(sh->keepCost.data(), r.cost, ncost * sizeof(int32_t));
+        if (r.sad) { memcpy(sh->keepSad.data(), r.sad, ncost * sizeof(int32_t)); memcpy(sh->keepSatd.data(), r.satd, ncost * sizeof(int32_t)); }
+    }
+    if (!o.noLog && o.allFrames) {   // 13.2 M lines per 1080p frame: one CTU (4.4 MB of text) per item, appended in POC order
+        if (!sh->costLog.begin(poc)) return false;
+        format_parallel(sh->costLog.f, sh->nCtus, 6u << 20, [&](LogBuf& b, int ctu) { write_frame_log(b, poc, true, r.cost, r.sad, r.satd, ctu, ctu + 1, sh->W, o.compat); });
+        sh->costLog.end();
+    }
+    if (!o.decisionsLog.empty()) {   // 726 300 lines per 1080p frame: 16 CTUs per item
+        if (!sh->decLog.begin(poc)) return false;
+        const int per = 16, items = (sh->nCtus + per - 1) / per;
+        format_parallel(sh->decLog.f, items, 8u << 20, [&](LogBuf& b, int it) { write_decisions(b, poc, bm, bc, sh->k, it * per, std::min(sh->nCtus, (it + 1) * per), sh->W); });
+        sh->decLog.end();
+    }
+    return true;
+}
+
 // one host thread per GPU: frames poc = g, g+G, g+2G, ...
 void gpu_worker(Shared* sh, mipb200_engine* e, mipb200_config cfg, int g, int G) {
     const Options& o = sh->opt;
-    const bool wantLog = !o.noLog, wantDec = !o.decisionsLog.empty();
-    const size_t fpx = (size_t)sh->W * sh->H, ncost = (size_t)sh->nCtus * MIP_COSTS_PER_CTU;
-    int next = g, done = g;
-    auto collect_one = [&]() -> bool {
-        mipb200_result r;
-        if (mipb200_collect(e, &r) != 0) { fprintf(stderr, "[!] ERROR (GPU %d): %s\n", cfg.device, mipb200_last_error()); sh->errors++; return false; }
-        const int poc = (int)r.poc;
-        if (sh->binFd >= 0) {   // raw table straight from the pinned ring to its place in the file (pwrite: any frame order, any thread)
-            const char* src = reinterpret_cast<const char*>(r.cost);
-            size_t left = ncost * sizeof(int32_t);
-            off_t off = (off_t)kBinHeader + (off_t)poc * (off_t)left;
-            while (left) {
-                const ssize_t w = pwrite(sh->binFd, src, left, off);
-                if (w <= 0) { perror("error while writing the binary log"); sh->errors++; return false; }
-                src += w; off += w; left -= (size_t)w;
-            }
-        }
-        if (wantLog && (poc == 0 || o.allFrames)) {   // the reference exports frame 0 only (main.cpp:1268)
-            memcpy(sh->keepCost[poc].data(), r.cost, ncost * sizeof(int32_t));
-            if (r.sad) { memcpy(sh->keepSad[poc].data(), r.sad, ncost * sizeof(int32_t)); memcpy(sh->keepSatd[poc].data(), r.satd, ncost * sizeof(int32_t)); }
-        }
-        if (wantDec) {
-            const size_t ncu = (size_t)sh->nCtus * MIP_CUS_PER_CTU * (r.top_k ? r.top_k : 1);
-            const uint8_t* bm = r.top_k ? r.topk_mode : r.best_mode;
-            const int32_t* bc = r.top_k ? r.topk_cost : r.best_cost;
-            memcpy(sh->keepMode[poc].data(), bm, ncu);
-            memcpy(sh->keepBest[poc].data(), bc, ncu * sizeof(int32_t));
-        }
-        done += G;
-        return true;
+    long next = g, done = g;
+    auto fail = [&](const char* what) {
+        if (what) fprintf(stderr, "[!] ERROR (GPU %d): %s\n", cfg.device, what);
+        sh->errors++;
+        sh->ring.fail();
+        sh->costLog.abort();
+        sh->decLog.abort();
     };
     while (done < o.nFrames) {
         while (next < o.nFrames && mipb200_in_flight(e) < cfg.slots) {
-            if (G == 1) printf("Current frame %d\n", next);
+            const uint16_t* frame = sh->ring.acquire(next);
+            if (!frame) { sh->errors++; return; }   // the reader failed (it said why)
+            if (G == 1) printf("Current frame %ld\n", next);
             if (sh->stamps) {
                 // The reference stamps every stage's enqueue (main.cpp:738-1216); here one fused kernel is every stage, so
                 // all stamps bracket the single asynchronous submit.  computeEnergy_NVIDIA.py:44-96 parses these names.
@@ -451,7 +613,7 @@ void gpu_worker(Shared* sh, mipb200_engine* e, mipb200_config cfg, int g, int G)
                 print_timestamp("START ENQUEUE upsamplePred_SIZEID=1");
                 print_timestamp("START ENQUEUE upsamplePred_SIZEID=0");
             }
-            const int rcs = mipb200_submit(e, sh->frames + fpx * next, next);
+            const int rcs = mipb200_submit(e, frame, next);
             if (sh->stamps) {
                 print_timestamp("FINISH WRITE SAMPLES MEMOBJ");
                 if (o.useAlt) print_timestamp("FINISH ENQUEUE filterFrame");
@@ -461,16 +623,37 @@ void gpu_worker(Shared* sh, mipb200_engine* e, mipb200_config cfg, int g, int G)
                 print_timestamp("FINISH ENQUEUE upsamplePred_SIZEID=1");
                 print_timestamp("FINISH ENQUEUE upsamplePred_SIZEID=0");
             }
-            if (rcs != 0) {
-                fprintf(stderr, "[!] ERROR (GPU %d): %s\n", cfg.device, mipb200_last_error());
-                sh->errors++;
-                return;
-            }
+            if (rcs != 0) { fail(mipb200_last_error()); return; }
             next += G;
         }
         if (sh->stamps) print_timestamp("START READ DISTORTION");
-        if (!collect_one()) break;
+        mipb200_result r;
+        if (mipb200_collect(e, &r) != 0) { fail(mipb200_last_error()); return; }
+        sh->ring.release((long)r.poc);        // the frame has been uploaded and used: its ring slot may be refilled
+        if (!consume_result(sh, r)) { fail(nullptr); return; }
+        done += G;
         if (sh->stamps && done < o.nFrames) print_timestamp("FINISH READ DISTORTION");
+    }
+}
+
+// streamed ring: frames in POC order into slot poc % capacity as slots are released
+void reader_thread(Shared* sh, FrameSource* src) {
+    FrameRing& ring = sh->ring;
+    const Options& o = sh->opt;
+    for (long poc = 0; poc < o.nFrames; ++poc) {
+        const int s = ring.slot_of(poc);
+        {
+            std::unique_lock<std::mutex> lk(ring.mu);
+            ring.cv.wait(lk, [&] { return ring.failed || !ring.busy[s]; });
+            if (ring.failed) return;
+        }
+        if (poc > 0 && poc % ring.period == 0) src->rewind_to_start();
+        if (!src->next(ring.slot_ptr(s))) { sh->errors++; ring.fail(); return; }
+        std::lock_guard<std::mutex> lk(ring.mu);
+        ring.holds[s] = poc;
+        ring.busy[s] = 1;
+        ring.filled = poc + 1;
+        ring.cv.notify_all();
     }
 }
 
@@ -515,26 +698,49 @@ int main(int argc, char** argv) {
     if (o.nFrames < 1 || o.numGpus < 1) { printf("  [!] ERROR: FramesToBeEncoded and NumGpus must be positive\n"); return 1; }
     if (o.topK < 0 || o.topK > MIPB200_TOPK_MAX) { printf("  [!] ERROR: TopK must be in 1..%d\n", MIPB200_TOPK_MAX); return 1; }
     if (o.bitDepth != 8 && o.bitDepth != 10 && o.bitDepth != 12) { printf("  [!] ERROR: BitDepth must be 8, 10 or 12\n"); return 1; }
-    if (o.topK > 1 && o.decisionsLog.empty()) { printf("  [!] ERROR: TopK needs --DecisionsLog\n"); return 1; }
-    sh.stamps = o.stageStamps < 0 ? (TRACE_POWER && o.numGpus == 1) : o.stageStamps != 0;
-    sh.W = W; sh.H = H; sh.nCtus = mipb200_num_ctus(W, H);
-
-    print_timestamp("START READ SAMPLES .csv");
-    std::vector<uint16_t> frames;
-    if (o.inputFormat == "csv") {
-        if (!read_frames_csv(o.input, W, H, o.nFrames, frames)) return 1;
-    } else if (o.inputFormat == "u16" || o.inputFormat == "yuv420p" || o.inputFormat == "yuv420p10le") {
-        if (!read_frames_binary(o.input, o.inputFormat, W, H, o.nFrames, frames)) return 1;
-    } else {
+    if (o.topK > 1 && o.decisionsLog.empty() && o.decisionsBin.empty()) { printf("  [!] ERROR: TopK needs --DecisionsLog\n"); return 1; }
+    if (o.inputFrames < 0 || o.ringFrames < 0) { printf("  [!] ERROR: InputFrames and RingFrames must be positive\n"); return 1; }
+    if (o.inputFormat != "csv" && o.inputFormat != "u16" && o.inputFormat != "yuv420p" && o.inputFormat != "yuv420p10le") {
         printf("  [!] ERROR: InputFormat %s not supported (csv, u16, yuv420p, yuv420p10le)\n", o.inputFormat.c_str());
         return 1;
     }
-    print_timestamp("FINISH READ SAMPLES .csv");
-    sh.frames = frames.data();
-    sh.keepCost.resize(o.nFrames); sh.keepSad.resize(o.nFrames); sh.keepSatd.resize(o.nFrames);
-    sh.keepMode.resize(o.nFrames); sh.keepBest.resize(o.nFrames);
+    sh.stamps = o.stageStamps < 0 ? (TRACE_POWER && o.numGpus == 1) : o.stageStamps != 0;
+    sh.W = W; sh.H = H; sh.nCtus = mipb200_num_ctus(W, H);
+    sh.k = o.topK > 1 ? o.topK : 1;
+    {
+        const bool wantLog = !o.noLog, wantDec = !o.decisionsLog.empty() || !o.decisionsBin.empty(), wantBin = !o.binaryLog.empty();
+        const bool wantCost = wantLog || wantBin || (!wantDec && o.digest.empty());    // nothing else asked for: the reference's table
+        sh.emit = (wantCost ? MIPB200_EMIT_COSTS : 0) | (wantLog && !o.compat ? MIPB200_EMIT_SAD_SATD : 0) | (wantDec || !wantCost || !o.digest.empty() ? MIPB200_EMIT_DECISIONS : 0);
+    }
 
-    // ---- timed window: first upload -> last result resident on the host (main.cpp:566-569, 1247-1250)
+    // ---- the frame ring: resident when the distinct frames fit, streamed otherwise
+    FrameRing& ring = sh.ring;
+    ring.fpx = (size_t)W * H;
+    ring.period = o.inputFrames > 0 ? std::min(o.inputFrames, o.nFrames) : o.nFrames;
+    {
+        const size_t frameBytes = ring.fpx * sizeof(uint16_t);
+        long cap = o.ringFrames > 0 ? o.ringFrames : (long)std::max<size_t>((size_t)4 * o.numGpus, ((size_t)2 << 30) / frameBytes);
+        cap = std::max<long>(cap, 4L * o.numGpus);
+        ring.resident = ring.period <= cap;
+        ring.capacity = (int)(ring.resident ? ring.period : cap);
+        void* mem = nullptr;
+        if (posix_memalign(&mem, 4096, frameBytes * (size_t)ring.capacity) != 0) {
+            printf("  [!] ERROR: cannot allocate the frame ring (%d frames of %zu bytes)\n", ring.capacity, frameBytes);
+            return 1;
+        }
+        ring.base = static_cast<uint16_t*>(mem);
+        ring.holds.assign(ring.capacity, -1);
+        ring.busy.assign(ring.capacity, 0);
+    }
+    FrameSource src;
+    print_timestamp("START READ SAMPLES .csv");
+    if (!src.open(o.input, o.inputFormat, W, H, o.bitDepth, ring.period)) return 1;
+    if (ring.resident) {   // like the reference: every (distinct) frame is in memory before the device is touched
+        for (int i = 0; i < ring.period; ++i)
+            if (!src.next(ring.slot_ptr(i))) return 1;
+    }
+    print_timestamp("FINISH READ SAMPLES .csv");
+
     {   // device selection banner of the reference (main.cpp:220-228); it exits with 0 on a bad index
         const int found = mipb200_device_count();
         if (found < 0) { fprintf(stderr, "[!] ERROR: %s\n", mipb200_last_error()); return 1; }
@@ -555,28 +761,47 @@ int main(int argc, char** argv) {
     }
     auto destroy_all = [&] { for (auto* e : engines) mipb200_destroy(e); };
     if (sh.errors) { destroy_all(); return 1; }
-    // host result arrays, allocated and touched here like the reference's return_* arrays (main.cpp:656-662)
-    {
-        const size_t ncost = (size_t)sh.nCtus * MIP_COSTS_PER_CTU, ncu = (size_t)sh.nCtus * MIP_CUS_PER_CTU * (o.topK > 1 ? o.topK : 1);
-        for (int poc = 0; poc < o.nFrames; ++poc) {
-            if (!o.noLog && (poc == 0 || o.allFrames)) {
-                sh.keepCost[poc].resize(ncost);
-                if (!o.compat) { sh.keepSad[poc].resize(ncost); sh.keepSatd[poc].resize(ncost); }
-            }
-            if (!o.decisionsLog.empty()) { sh.keepMode[poc].resize(ncu); sh.keepBest[poc].resize(ncu); }
-        }
+    const size_t ncost = (size_t)sh.nCtus * MIP_COSTS_PER_CTU;
+    // frame 0's tables for the reference's log, allocated and touched here like its return_* arrays (main.cpp:656-662)
+    if (!o.noLog && !o.allFrames) {
+        sh.keepCost.assign(ncost, 0);
+        if (!o.compat) { sh.keepSad.assign(ncost, 0); sh.keepSatd.assign(ncost, 0); }
     }
-    if (!o.binaryLog.empty()) {
-        sh.binFd = open(o.binaryLog.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
-        if (sh.binFd < 0) { perror("error while opening the binary log"); destroy_all(); return 1; }
+    if (!o.digest.empty()) { sh.digCost.assign(o.nFrames, 0); sh.digMode.assign(o.nFrames, 0); sh.digBest.assign(o.nFrames, 0); }
+    auto open_bin = [&](const std::string& path, const char* magic, uint32_t perCtu, const char* what) -> int {
+        const int fd = open(path.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+        if (fd < 0) { perror(what); return -1; }
         uint32_t hdr[kBinHeader / 4] = {0};
-        memcpy(hdr, "MIPB200C", 8);
+        memcpy(hdr, magic, 8);
         hdr[2] = 1; hdr[3] = (uint32_t)W; hdr[4] = (uint32_t)H; hdr[5] = (uint32_t)o.nFrames; hdr[6] = (uint32_t)sh.nCtus;
-        hdr[7] = MIP_COSTS_PER_CTU; hdr[8] = (uint32_t)o.bitDepth; hdr[9] = (uint32_t)sh.filterType; hdr[10] = (uint32_t)o.kernelIdx;
-        if (pwrite(sh.binFd, hdr, sizeof(hdr), 0) != (ssize_t)sizeof(hdr)) { perror("error while writing the binary log"); destroy_all(); return 1; }
+        hdr[7] = perCtu; hdr[8] = (uint32_t)o.bitDepth; hdr[9] = (uint32_t)sh.filterType; hdr[10] = (uint32_t)o.kernelIdx; hdr[11] = (uint32_t)sh.k;
+        if (pwrite(fd, hdr, sizeof(hdr), 0) != (ssize_t)sizeof(hdr)) { perror(what); close(fd); return -1; }
+        return fd;
+    };
+    if (!o.binaryLog.empty() && (sh.binFd = open_bin(o.binaryLog, "MIPB200C", MIP_COSTS_PER_CTU, "error while opening the binary log")) < 0) { destroy_all(); return 1; }
+    if (!o.decisionsBin.empty() && (sh.decFd = open_bin(o.decisionsBin, "MIPB200D", MIP_CUS_PER_CTU, "error while opening the binary decisions")) < 0) { destroy_all(); return 1; }
+    if (!o.noLog && o.allFrames) {
+        const std::string name = o.prefix + ".csv";
+        if (!(sh.costLog.f = fopen(name.c_str(), "w"))) { perror("error while opening the output file"); destroy_all(); return 1; }
+        fputs("POC,CTU,cuSizeName,W,H,CU,X,Y,Mode,SAD,SATD,minSadHad\n", sh.costLog.f);
     }
-    // page-lock the frames so that every upload is a DMA from where the samples already are (no staging copy)
-    const bool pinned = mipb200_pin_host(frames.data(), frames.size() * sizeof(uint16_t)) == 0;
+    if (!o.decisionsLog.empty()) {
+        if (!(sh.decLog.f = fopen(o.decisionsLog.c_str(), "w"))) { perror("error while opening the decisions log"); destroy_all(); return 1; }
+        std::string hdr = "POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost";
+        for (int j = 2; j <= sh.k; ++j) hdr += ",Mode" + std::to_string(j) + ",Cost" + std::to_string(j);
+        hdr += "\n";
+        fputs(hdr.c_str(), sh.decLog.f);
+    }
+    // page-lock the ring so that every upload is a DMA from where the samples already are (no staging copy)
+    ring.pinned = mipb200_pin_host_on(o.deviceIndex, ring.base, ring.fpx * sizeof(uint16_t) * (size_t)ring.capacity) == 0;
+    std::thread reader;
+    if (!ring.resident) {   // fill the ring before the window opens; from then on the reader refills released slots
+        reader = std::thread(reader_thread, &sh, &src);
+        std::unique_lock<std::mutex> lk(ring.mu);
+        ring.cv.wait(lk, [&] { return ring.failed || ring.filled >= std::min<long>(ring.capacity, o.nFrames); });
+    }
+    printf("Frame ring: %d x %.1f MB %s, %s\n", ring.capacity, ring.fpx * 2 / 1e6, ring.pinned ? "page-locked" : "pageable",
+           ring.resident ? "resident (every distinct frame loaded before the timed window)" : "streamed by a reader thread");
     print_timestamp("FINISH BUILD KERNELS");
 
     std::vector<unsigned long long> mj0(o.numGpus, 0), mj1(o.numGpus, 0);
@@ -586,6 +811,7 @@ int main(int argc, char** argv) {
             printf("  [!] Energy counter unavailable: %s\n", mipb200_last_error());
             haveEnergy = false;
         }
+    // ---- timed window: first upload -> last result consumed on the host (main.cpp:566-569, 1247-1250)
     print_timestamp("START WRITE SAMPLES MEMOBJ");
     const double t0 = now_ms();
     {
@@ -597,42 +823,38 @@ int main(int argc, char** argv) {
     print_timestamp("FINISH READ DISTORTION");
     for (int g = 0; g < o.numGpus && haveEnergy; ++g)
         if (mipb200_device_energy_mj(o.deviceIndex + g, &mj1[g]) != 0) haveEnergy = false;
+    if (reader.joinable()) { if (sh.errors) ring.fail(); reader.join(); }
     destroy_all();
     if (sh.binFd >= 0) close(sh.binFd);
-    if (pinned) mipb200_unpin_host(frames.data());
+    if (sh.decFd >= 0) close(sh.decFd);
+    if (sh.costLog.f) fclose(sh.costLog.f);
+    if (sh.decLog.f) fclose(sh.decLog.f);
+    if (ring.pinned) mipb200_unpin_host(ring.base);
+    free(ring.base);
     if (sh.errors) return 1;
 
-    if (!o.noLog) {
+    if (!o.noLog && !o.allFrames) {
         // like the reference, a log is written even when -l is omitted (file ".csv", main.cpp:1264-1269)
         std::string name = o.prefix + ".csv";
         FILE* f = fopen(name.c_str(), "w");
         if (!f) { perror("error while opening the output file"); return 1; }
-        LogBuf lb(f);
-        const char* hdr = o.allFrames ? "POC,CTU,cuSizeName,W,H,CU,X,Y,Mode,SAD,SATD,minSadHad\n" : "CTU,cuSizeName,W,H,CU,X,Y,Mode,SAD,SATD,minSadHad\n";
-        lb.put(hdr, strlen(hdr));
-        lb.flush();
+        fputs("CTU,cuSizeName,W,H,CU,X,Y,Mode,SAD,SATD,minSadHad\n", f);
         // 13.2 M lines per 1080p frame: CTUs are formatted by all host threads into private buffers (one CTU = 4.4 MB of
         // text each) and written in CTU order
-        for (int poc = 0; poc < (o.allFrames ? o.nFrames : 1); ++poc) {
-            const int32_t* cst = sh.keepCost[poc].data();
-            const int32_t* sd = sh.keepSad[poc].empty() ? nullptr : sh.keepSad[poc].data();
-            const int32_t* st = sh.keepSatd[poc].empty() ? nullptr : sh.keepSatd[poc].data();
-            format_parallel(f, sh.nCtus, 6u << 20, [&](LogBuf& b, int ctu) { write_frame_log(b, poc, o.allFrames, cst, sd, st, ctu, ctu + 1, W, o.compat); });
-        }
+        const int32_t* sd = sh.keepSad.empty() ? nullptr : sh.keepSad.data();
+        const int32_t* st = sh.keepSatd.empty() ? nullptr : sh.keepSatd.data();
+        format_parallel(f, sh.nCtus, 6u << 20, [&](LogBuf& b, int ctu) { write_frame_log(b, 0, false, sh.keepCost.data(), sd, st, ctu, ctu + 1, W, o.compat); });
         fclose(f);
     }
-
-    if (!o.decisionsLog.empty()) {
-        FILE* f = fopen(o.decisionsLog.c_str(), "w");
-        if (!f) { perror("error while opening the decisions log"); return 1; }
-        LogBuf lb(f);
-        const int k = o.topK > 1 ? o.topK : 1;
-        std::string hdr = "POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost";
-        for (int j = 2; j <= k; ++j) hdr += ",Mode" + std::to_string(j) + ",Cost" + std::to_string(j);
-        hdr += "\n";
-        lb.put(hdr.c_str(), hdr.size());
-        lb.flush();
-        format_parallel(f, o.nFrames, 8u << 20, [&](LogBuf& b, int poc) { write_decisions(b, poc, sh.keepMode[poc].data(), sh.keepBest[poc].data(), k, 0, sh.nCtus, W); });
+    if (!o.digest.empty()) {
+        FILE* f = fopen(o.digest.c_str(), "w");
+        if (!f) { perror("error while opening the digest file"); return 1; }
+        const bool haveCost = sh.emit & MIPB200_EMIT_COSTS;
+        fprintf(f, "POC,%sModes,BestCosts\n", haveCost ? "Costs," : "");
+        for (int poc = 0; poc < o.nFrames; ++poc) {
+            if (haveCost) fprintf(f, "%d,%016llx,%016llx,%016llx\n", poc, (unsigned long long)sh.digCost[poc], (unsigned long long)sh.digMode[poc], (unsigned long long)sh.digBest[poc]);
+            else fprintf(f, "%d,%016llx,%016llx\n", poc, (unsigned long long)sh.digMode[poc], (unsigned long long)sh.digBest[poc]);
+        }
         fclose(f);
     }
 
@@ -642,6 +864,10 @@ int main(int argc, char** argv) {
     printf("Elapsed time (ms) from writing samples to reading distortion (%dx), %d\n", o.nFrames, (int)lround(t1 - t0));
     printf("=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=-=\n\n");
     printf("Throughput: %.1f frames/s on %d GPU(s)\n", o.nFrames * 1e3 / (t1 - t0 > 0 ? t1 - t0 : 1e-3), o.numGpus);
+    {
+        struct rusage ru;
+        if (getrusage(RUSAGE_SELF, &ru) == 0) printf("Peak host memory (MB), %.0f\n", ru.ru_maxrss / 1024.0);   // does not grow with -f: ring + engines' rings
+    }
     if (o.energy && haveEnergy) {
         // the board's own energy counter over the timed window (the reference integrates an nvidia-smi power trace
         // between the same two stamps, computeEnergy_NVIDIA.py:98-140)

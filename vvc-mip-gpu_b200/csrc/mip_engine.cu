@@ -10,8 +10,11 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost a pointer test unless a profiler (nsys / ncu --nvtx) is attached
 
 #include "../../include/mipb200.h"
 #include "mip_kernels.h"
@@ -56,12 +59,46 @@ struct Slot {
 std::mutex g_init_mutex;
 bool g_dev_init[64] = {false};
 
+// Every exported function that touches the device switches to the engine's GPU and puts the caller's current device
+// back on return: a host application (torch, another engine) must not find its thread's device changed under it.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != dev) err = cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Host ranges page-locked through mipb200_pin_host(): submit recognises them without asking the driver.
+struct PinnedRange { const char* lo; const char* hi; };
+std::mutex g_pin_mutex;
+std::vector<PinnedRange> g_pinned;
+
+bool in_pinned_registry(const void* p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_pin_mutex);
+    const char* c = static_cast<const char*>(p);
+    for (const PinnedRange& r : g_pinned)
+        if (c >= r.lo && c + bytes <= r.hi) return true;
+    return false;
+}
+
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 }  // namespace
 
 struct mipb200_engine {
     mipb200_config cfg;
     int n_ctus = 0;
     size_t frame_bytes = 0, cost_bytes = 0, cu_bytes4 = 0, cu_bytes1 = 0;
+    // cfg.slots frames may be in flight; the ring has ONE MORE slot than that, so that the slot whose results the last
+    // mipb200_collect() exposed is never the one the next mipb200_submit() writes into: result pointers stay valid until
+    // the next collect, as include/mipb200.h promises.
     std::vector<Slot> slots;
     int head = 0;   // next slot to submit into
     int tail = 0;   // oldest slot in flight
@@ -133,7 +170,7 @@ static void free_slot(Slot& s) {
 
 MIPB200_API void mipb200_destroy(mipb200_engine* e) {
     if (!e) return;
-    cudaSetDevice(e->cfg.device);
+    DeviceGuard dg(e->cfg.device);
     for (auto& s : e->slots) free_slot(s);
     if (e->aux_stream) { cudaStreamSynchronize(e->aux_stream); cudaStreamDestroy(e->aux_stream); }
     delete e;
@@ -149,13 +186,38 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
     if (ce != cudaSuccess || ndev == 0)
         return fail(MIPB200_ENODEV, "no CUDA device: %s (this engine has no CPU fallback)", cudaGetErrorString(ce));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(MIPB200_ENODEV, "device %d not in 0..%d", cfg->device, ndev - 1);
-    CU_TRY(cudaSetDevice(cfg->device));
+    if (cfg->device >= (int)(sizeof(g_dev_init) / sizeof(g_dev_init[0]))) return fail(MIPB200_ENODEV, "device %d: at most %d devices are supported", cfg->device, (int)(sizeof(g_dev_init) / sizeof(g_dev_init[0])));
+    DeviceGuard dg(cfg->device);
+    CU_TRY(dg.err);
     {
         std::lock_guard<std::mutex> lk(g_init_mutex);
         if (!g_dev_init[cfg->device]) {
-            const char* ev = getenv("MIPB200_CHUNKS");
-            int chunks = ev ? atoi(ev) : 3;   // chunks per CTU half: 3 is the throughput optimum with frames overlapping on the slot streams (0.444 vs 0.454 ms with 4; a lone frame prefers 4: 0.485 vs 0.522 ms)
-            CU_TRY(mipb200::kernels_init(chunks));
+            // chunks per CTU half (= CTAs per half): 3 equal shares are the throughput optimum with frames overlapping on the
+            // slot streams (0.444 vs 0.454 ms with 4; a lone frame prefers 4: 0.485 vs 0.522 ms).  Tuning knobs, not API:
+            // MIPB200_CHUNKS=n (equal shares), MIPB200_CHUNK_WEIGHTS=a,b,c,.. (relative cost shares in launch order).
+            int chunks = 3;
+            double weights[64];
+            bool haveW = false;
+            if (const char* ew = getenv("MIPB200_CHUNK_WEIGHTS")) {
+                chunks = 0;
+                for (const char* p = ew; *p && chunks < 64;) {
+                    char* end = nullptr;
+                    const double w = strtod(p, &end);
+                    if (end == p || !(w > 0)) return fail(MIPB200_EINVAL, "MIPB200_CHUNK_WEIGHTS=\"%s\": need positive numbers separated by commas", ew);
+                    weights[chunks++] = w;
+                    p = *end == ',' ? end + 1 : end;
+                    if (*end && *end != ',') return fail(MIPB200_EINVAL, "MIPB200_CHUNK_WEIGHTS=\"%s\": need positive numbers separated by commas", ew);
+                }
+                haveW = chunks > 0;
+            } else if (const char* ev = getenv("MIPB200_CHUNKS")) {
+                chunks = atoi(ev);
+            }
+            if (chunks < 2 || chunks > 64)
+                return fail(MIPB200_EINVAL, "%d chunks per CTU half: need 2..64 (one chunk would hold more CUs than the kernel's decision table)", chunks);
+            const cudaError_t ke = mipb200::kernels_init(chunks, haveW ? weights : nullptr);
+            if (ke == cudaErrorInvalidValue)
+                return fail(MIPB200_EINVAL, "this split into %d chunks puts more than 2048 CUs into one chunk; use more chunks or more even weights", chunks);
+            CU_TRY(ke);
             g_dev_init[cfg->device] = true;
         }
     }
@@ -167,7 +229,7 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
     e->cost_bytes = (size_t)e->n_ctus * MIP_COSTS_PER_CTU * sizeof(int32_t);
     e->cu_bytes4 = (size_t)e->n_ctus * MIP_CUS_PER_CTU * sizeof(int32_t);
     e->cu_bytes1 = (size_t)e->n_ctus * MIP_CUS_PER_CTU;
-    e->slots.resize(cfg->slots);
+    e->slots.resize(cfg->slots + 1);
     if (mipb200::make_filter_params(cfg->filter_type, cfg->kernel_idx, e->cfg.bit_depth, &e->fp) != cudaSuccess) {
         delete e;
         return fail(MIPB200_EINVAL, "filter parameters of filter_type %d kernel_idx %d failed their exactness check", cfg->filter_type, cfg->kernel_idx);
@@ -190,8 +252,7 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
         E_TRY(cudaEventCreate(&s.ev_k0));
         E_TRY(cudaEventCreate(&s.ev_k1));
         E_TRY(cudaEventCreate(&s.ev_done));
-        E_TRY(cudaHostAlloc((void**)&s.h_frame, e->frame_bytes, cudaHostAllocDefault));
-        E_TRY(cudaMalloc((void**)&s.d_frame, e->frame_bytes));
+        E_TRY(cudaMalloc((void**)&s.d_frame, e->frame_bytes));   // the pinned staging frame is allocated on first use (slot_staging)
         if (wc || tk) {   // decisions-only engines never materialise the 97840-entry table; a top-k shortlist reads it
             E_TRY(cudaMalloc((void**)&s.d_cost, e->cost_bytes));
             if (wc) E_TRY(cudaHostAlloc((void**)&s.h_cost, e->cost_bytes, cudaHostAllocDefault));
@@ -223,9 +284,19 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
 MIPB200_API int mipb200_in_flight(const mipb200_engine* e) { return e ? e->in_flight : 0; }
 MIPB200_API long long mipb200_kernel_launches(const mipb200_engine* e) { return e ? e->launches : 0; }
 
+// pinned staging frame of a slot: only callers that hand over pageable memory or fill mipb200_next_input() need one
+static uint16_t* slot_staging(mipb200_engine* e, Slot& s) {
+    if (!s.h_frame && cudaHostAlloc((void**)&s.h_frame, e->frame_bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        s.h_frame = nullptr;
+    }
+    return s.h_frame;
+}
+
 MIPB200_API uint16_t* mipb200_next_input(mipb200_engine* e) {
-    if (!e || e->in_flight >= (int)e->slots.size()) return nullptr;
-    return e->slots[e->head].h_frame;
+    if (!e || e->in_flight >= e->cfg.slots) return nullptr;
+    DeviceGuard dg(e->cfg.device);
+    return slot_staging(e, e->slots[e->head]);
 }
 
 // one fused kernel per frame: (filter +) boundaries + prediction + costs + per-CU argmin; counts launches
@@ -239,16 +310,26 @@ static int enqueue_kernels(mipb200_engine* e, const uint16_t* d_frame, int32_t* 
 
 MIPB200_API int mipb200_submit(mipb200_engine* e, const uint16_t* frame, int64_t poc) {
     if (!e || !frame) return fail(MIPB200_EINVAL, "engine or frame is NULL");
-    if (e->in_flight >= (int)e->slots.size()) return fail(MIPB200_EBUSY, "all %d slots in flight; collect first", (int)e->slots.size());
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    if (e->in_flight >= e->cfg.slots) return fail(MIPB200_EBUSY, "all %d slots in flight; collect first", e->cfg.slots);
+    NvtxRange nv("mipb200_submit");
+    DeviceGuard dg(e->cfg.device);
+    CU_TRY(dg.err);
     Slot& s = e->slots[e->head];
     // Source of the H2D DMA: the slot's own pinned buffer, the caller's buffer if that is page-locked already
-    // (cudaHostAlloc / cudaHostRegister / torch pin_memory: no staging copy), else a staging copy of pageable memory.
-    const uint16_t* src = s.h_frame;
-    if (frame != s.h_frame) {
+    // (mipb200_pin_host / cudaHostAlloc / cudaHostRegister / torch pin_memory: no staging copy), else a staging copy of
+    // pageable memory.  Device and managed pointers are refused: this is the host path (mipb200_run_device is the other).
+    const uint16_t* src = frame;
+    if (frame != s.h_frame && !in_pinned_registry(frame, e->frame_bytes)) {
         cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, frame) == cudaSuccess && attr.type == cudaMemoryTypeHost) src = frame;
-        else { cudaGetLastError(); memcpy(s.h_frame, frame, e->frame_bytes); }
+        const cudaError_t pe = cudaPointerGetAttributes(&attr, frame);
+        if (pe != cudaSuccess) cudaGetLastError();
+        if (pe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged))
+            return fail(MIPB200_EINVAL, "mipb200_submit takes a host frame; %s memory goes through mipb200_run_device", attr.type == cudaMemoryTypeDevice ? "device" : "managed");
+        if (pe != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+            if (!slot_staging(e, s)) return fail(MIPB200_ENOMEM, "cannot allocate the pinned staging frame (%zu bytes)", e->frame_bytes);
+            memcpy(s.h_frame, frame, e->frame_bytes);
+            src = s.h_frame;
+        }
     }
     s.poc = poc;
     CU_TRY(cudaEventRecord(s.ev_start, s.stream));
@@ -284,7 +365,9 @@ MIPB200_API int mipb200_submit(mipb200_engine* e, const uint16_t* frame, int64_t
 MIPB200_API int mipb200_collect(mipb200_engine* e, mipb200_result* out) {
     if (!e || !out) return fail(MIPB200_EINVAL, "engine or result is NULL");
     if (e->in_flight == 0) return fail(MIPB200_EEMPTY, "nothing in flight");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    NvtxRange nv("mipb200_collect");
+    DeviceGuard dg(e->cfg.device);
+    CU_TRY(dg.err);
     Slot& s = e->slots[e->tail];
     CU_TRY(cudaEventSynchronize(s.ev_done));
     float ms = 0.f;
@@ -312,7 +395,8 @@ MIPB200_API int mipb200_run_device(mipb200_engine* e, const uint16_t* d_frame, i
     if (!d_cost && !d_best_mode) return fail(MIPB200_EINVAL, "at least one of d_cost and d_best_mode/d_best_cost is required");
     if ((d_best_mode == nullptr) != (d_best_cost == nullptr)) return fail(MIPB200_EINVAL, "d_best_mode and d_best_cost go together");
     if ((d_sad == nullptr) != (d_satd == nullptr)) return fail(MIPB200_EINVAL, "d_sad and d_satd go together");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    DeviceGuard dg(e->cfg.device);
+    CU_TRY(dg.err);
     cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
     return enqueue_kernels(e, d_frame, d_cost, d_sad, d_satd, d_best_mode, d_best_cost, st);
 }
@@ -320,7 +404,8 @@ MIPB200_API int mipb200_run_device(mipb200_engine* e, const uint16_t* d_frame, i
 MIPB200_API int mipb200_filter_device(mipb200_engine* e, const uint16_t* d_frame, uint16_t* d_out, void* stream) {
     if (!e || !d_frame || !d_out) return fail(MIPB200_EINVAL, "engine, d_frame and d_out are required");
     if (!e->cfg.filter_type) return fail(MIPB200_EINVAL, "engine was created with filter_type 0");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    DeviceGuard dg(e->cfg.device);
+    CU_TRY(dg.err);
     cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
     CU_TRY(mipb200::launch_filter(d_frame, d_out, e->cfg.width, e->cfg.height, e->cfg.filter_type, e->cfg.kernel_idx, st));
     e->launches++;
@@ -329,7 +414,8 @@ MIPB200_API int mipb200_filter_device(mipb200_engine* e, const uint16_t* d_frame
 
 MIPB200_API int mipb200_decide_device(mipb200_engine* e, const int32_t* d_cost, uint8_t* d_best_mode, int32_t* d_best_cost, void* stream) {
     if (!e || !d_cost || !d_best_mode || !d_best_cost) return fail(MIPB200_EINVAL, "NULL argument");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    DeviceGuard dg(e->cfg.device);
+    CU_TRY(dg.err);
     cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
     CU_TRY(mipb200::launch_decide(d_cost, e->n_ctus, d_best_mode, d_best_cost, st));
     e->launches++;
@@ -339,21 +425,34 @@ MIPB200_API int mipb200_decide_device(mipb200_engine* e, const int32_t* d_cost, 
 MIPB200_API int mipb200_topk_device(mipb200_engine* e, const int32_t* d_cost, int k, uint8_t* d_modes, int32_t* d_costs, void* stream) {
     if (!e || !d_cost || !d_modes || !d_costs) return fail(MIPB200_EINVAL, "NULL argument");
     if (k < 1 || k > MIPB200_TOPK_MAX) return fail(MIPB200_EINVAL, "k %d out of range 1..%d", k, MIPB200_TOPK_MAX);
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    DeviceGuard dg(e->cfg.device);
+    CU_TRY(dg.err);
     cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
     CU_TRY(mipb200::launch_topk(d_cost, e->n_ctus, k, d_modes, d_costs, st));
     e->launches++;
     return MIPB200_OK;
 }
 
-MIPB200_API int mipb200_pin_host(void* ptr, size_t bytes) {
+MIPB200_API int mipb200_pin_host_on(int device, void* ptr, size_t bytes) {
     if (!ptr || !bytes) return fail(MIPB200_EINVAL, "ptr and bytes are required");
-    CU_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    int cur = 0;
+    if (device < 0) { CU_TRY(cudaGetDevice(&cur)); device = cur; }
+    DeviceGuard dg(device);
+    CU_TRY(dg.err);
+    CU_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));   // portable: every device's engine may DMA from it
+    std::lock_guard<std::mutex> lk(g_pin_mutex);
+    g_pinned.push_back({static_cast<const char*>(ptr), static_cast<const char*>(ptr) + bytes});
     return MIPB200_OK;
 }
 
+MIPB200_API int mipb200_pin_host(void* ptr, size_t bytes) { return mipb200_pin_host_on(-1, ptr, bytes); }
+
 MIPB200_API int mipb200_unpin_host(void* ptr) {
     if (!ptr) return fail(MIPB200_EINVAL, "ptr is NULL");
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mutex);
+        g_pinned.erase(std::remove_if(g_pinned.begin(), g_pinned.end(), [&](const PinnedRange& r) { return r.lo == static_cast<const char*>(ptr); }), g_pinned.end());
+    }
     CU_TRY(cudaHostUnregister(ptr));
     return MIPB200_OK;
 }
@@ -393,7 +492,8 @@ MIPB200_API int mipb200_device_energy_mj(int device, unsigned long long* millijo
 
 MIPB200_API int mipb200_sync(mipb200_engine* e) {
     if (!e) return fail(MIPB200_EINVAL, "engine is NULL");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+    DeviceGuard dg(e->cfg.device);
+    CU_TRY(dg.err);
     for (auto& s : e->slots) CU_TRY(cudaStreamSynchronize(s.stream));
     CU_TRY(cudaStreamSynchronize(e->aux_stream));
     return MIPB200_OK;

@@ -32,6 +32,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "mip_filters.h"
@@ -480,6 +481,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // one 2-D box of the frame -> shared memory; completion (bytes) is counted on `bar`
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -637,10 +643,12 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         for (int i = tid; i < MAT_BYTES / 4; i += NT)
             reinterpret_cast<uint32_t*>(s_mat)[i] = reinterpret_cast<const uint32_t*>(g_mat)[i];
         __syncthreads();                                  // the barrier word is initialised for everyone
-        {
-            int spins = 0;
+        if (!mbar_try_wait(s_bar, 0)) {
+            // a lost TMA must not hang the GPU: give up after 4 s of wall time (time-based, so that a sanitizer or a
+            // debugger slowing the kernel down by orders of magnitude cannot trip it)
+            const uint64_t t0 = globaltimer_ns();
             while (!mbar_try_wait(s_bar, 0))
-                if (++spins > (1 << 22)) __trap();        // a lost TMA must not hang the GPU
+                if (globaltimer_ns() - t0 > 4000000000ull) __trap();
         }
         // ---- originals (+1) as int32 (see diff_shifted()); rows below the frame are TMA zero fill
         for (int i = tid; i < TILE_ROWS * 16; i += NT) {
@@ -891,9 +899,14 @@ mip_topk_kernel(const int32_t* __restrict__ cost, int n_ctus, int k, uint8_t* __
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
-cudaError_t kernels_init(int chunks) {
+cudaError_t kernels_init(int chunks, const double* weights) {
     if (chunks < 1) chunks = 1;
     if (chunks > MAX_CHUNKS) chunks = MAX_CHUNKS;
+    // cum[k] = share of a half's cost that lies before chunk k (equal shares unless weights are given)
+    double cum[MAX_CHUNKS + 1], wsum = 0;
+    for (int k = 0; k < chunks; ++k) wsum += weights ? weights[k] : 1.0;
+    cum[0] = 0;
+    for (int k = 0; k < chunks; ++k) cum[k + 1] = cum[k] + (weights ? weights[k] : 1.0) / wsum;
     cudaError_t err;
     // CU tables
     DevType types[MIP_NUM_TYPES];
@@ -960,7 +973,7 @@ cudaError_t kernels_init(int chunks) {
         chunk_ord[hf][0] = 0;
         for (size_t i = 0; i < work[hf].size() && k < chunks; ++i) {
             acc += wcost[hf][i];
-            if (acc >= total * k / chunks && cut_ok[hf][i]) { chunk_ord[hf][k] = (uint16_t)ord_after[hf][i]; begin[hf][k++] = (int)i + 1; }
+            if (acc >= total * cum[k] && cut_ok[hf][i]) { chunk_ord[hf][k] = (uint16_t)ord_after[hf][i]; begin[hf][k++] = (int)i + 1; }
         }
         while (k <= MAX_CHUNKS) { chunk_ord[hf][k] = (uint16_t)ord_total[hf]; begin[hf][k++] = (int)work[hf].size(); }
         for (int q = 0; q < chunks; ++q)
@@ -1014,7 +1027,19 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
+// A tensor map depends on nothing but (address, W, H), so encoded maps are kept: the engine's slots and a caller's
+// resident frame pool hit the cache on every launch after their first (no driver call per frame).
+struct MapCacheEntry { const uint16_t* ptr; int W, H; CUtensorMap map; };
+static std::mutex g_map_mutex;
+static MapCacheEntry g_map_cache[64];
+static int g_map_count = 0, g_map_next = 0;
+
 static cudaError_t make_frame_map(const uint16_t* d_frame, int W, int H, CUtensorMap* map) {
+    {
+        std::lock_guard<std::mutex> lk(g_map_mutex);
+        for (int i = 0; i < g_map_count; ++i)
+            if (g_map_cache[i].ptr == d_frame && g_map_cache[i].W == W && g_map_cache[i].H == H) { *map = g_map_cache[i].map; return cudaSuccess; }
+    }
     if (!g_encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -1030,7 +1055,13 @@ static cudaError_t make_frame_map(const uint16_t* d_frame, int W, int H, CUtenso
     const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t*>(d_frame), gdim, gstride, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    MapCacheEntry& en = g_map_cache[g_map_next];
+    en.ptr = d_frame; en.W = W; en.H = H; en.map = *map;
+    g_map_next = (g_map_next + 1) % 64;
+    if (g_map_count < 64) ++g_map_count;
+    return cudaSuccess;
 }
 
 cudaError_t make_filter_params(int ft, int kidx, int bit_depth, FilterParams* fp) {

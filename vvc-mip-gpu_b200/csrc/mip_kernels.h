@@ -6,7 +6,9 @@
 namespace mipb200 {
 
 // One-time per device: packs the MIP matrices, the CU tables and the work list into device memory.
-cudaError_t kernels_init(int chunks_per_ctu);
+// chunks = CTAs per CTU half; weights (optional, `chunks` entries) = relative cost share of each chunk, in launch order.
+// cudaErrorInvalidValue: a chunk would hold more CUs than the shared-memory decision table (use more chunks).
+cudaError_t kernels_init(int chunks_per_half, const double* weights = nullptr);
 int kernels_chunks_per_ctu();
 
 // Low-pass filter of the fused path, prepared once per engine and passed to the kernel by value (constant-bank

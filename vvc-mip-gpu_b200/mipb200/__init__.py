@@ -33,7 +33,7 @@ TOPK_MAX = 12
 ABI_SYMBOLS = (
     "mipb200_create", "mipb200_destroy", "mipb200_next_input", "mipb200_submit", "mipb200_collect",
     "mipb200_in_flight", "mipb200_num_ctus", "mipb200_device_count", "mipb200_run_device", "mipb200_filter_device",
-    "mipb200_decide_device", "mipb200_topk_device", "mipb200_kernel_launches", "mipb200_device_energy_mj", "mipb200_pin_host", "mipb200_unpin_host", "mipb200_sync", "mipb200_last_error",
+    "mipb200_decide_device", "mipb200_topk_device", "mipb200_kernel_launches", "mipb200_device_energy_mj", "mipb200_pin_host", "mipb200_pin_host_on", "mipb200_unpin_host", "mipb200_sync", "mipb200_last_error",
     "mipb200_version",
 )
 
@@ -112,6 +112,8 @@ def lib() -> ctypes.CDLL:
         L.mipb200_device_energy_mj.restype = ctypes.c_int
         L.mipb200_pin_host.argtypes = [vp, ctypes.c_size_t]
         L.mipb200_pin_host.restype = ctypes.c_int
+        L.mipb200_pin_host_on.argtypes = [ctypes.c_int, vp, ctypes.c_size_t]
+        L.mipb200_pin_host_on.restype = ctypes.c_int
         L.mipb200_unpin_host.argtypes = [vp]
         L.mipb200_unpin_host.restype = ctypes.c_int
         L.mipb200_sync.argtypes = [vp]
@@ -171,6 +173,7 @@ class Engine:
         _check(lib().mipb200_create(ctypes.byref(self._h), ctypes.byref(self.cfg)))
         self.width, self.height = width, height
         self.n_ctus = lib().mipb200_num_ctus(width, height)
+        self._pending = []              # frames in flight, oldest first
 
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:
@@ -201,10 +204,13 @@ class Engine:
         if frame.dtype != np.uint16 or frame.shape != (self.height, self.width) or not frame.flags.c_contiguous:
             raise ValueError("frame must be C-contiguous uint16 [height, width]")
         _check(lib().mipb200_submit(self._h, frame.ctypes.data, poc))
+        self._pending.append(frame)     # a page-locked frame is DMA'd in place: keep it alive until it has been collected
 
     def collect(self) -> FrameResult:
         r = Result()
         _check(lib().mipb200_collect(self._h, ctypes.byref(r)))
+        if self._pending:
+            self._pending.pop(0)
         return FrameResult(r)
 
     def in_flight(self) -> int:

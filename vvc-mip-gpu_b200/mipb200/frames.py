@@ -107,3 +107,24 @@ def read_cost_dump(path: str):
                    bit_depth=int(v[6]), filter_type=int(v[7]), kernel_idx=int(v[8]))
         data = np.fromfile(f, dtype="<i4")
     return hdr, data.reshape(hdr["frames"], hdr["n_ctus"], hdr["costs_per_ctu"])
+
+
+def read_decisions_dump(path: str):
+    """Reads a `mipb200_main --DecisionsBin` file -> (header dict, uint8 modes [frames][nCTU][5380][k], int32 costs, same shape).
+    Layout: 64-byte header = "MIPB200D", then little-endian u32 version, width, height, frames, CTUs, CUs per CTU, bit depth,
+    filter type, kernel index, k (entries per CU: 1, or --TopK); then one record per frame in POC order: the modes of every
+    CU (uint8, 0xFF = CU not inside the frame) followed by their costs (int32, -1), both in [CTU][CU][k] order."""
+    with open(path, "rb") as f:
+        raw = f.read(64)
+        if len(raw) != 64 or raw[:8] != b"MIPB200D":
+            raise ValueError(f"{path} is not a mipb200 decisions dump")
+        v = np.frombuffer(raw[8:48], dtype="<u4")
+        hdr = dict(version=int(v[0]), width=int(v[1]), height=int(v[2]), frames=int(v[3]), n_ctus=int(v[4]), cus_per_ctu=int(v[5]),
+                   bit_depth=int(v[6]), filter_type=int(v[7]), kernel_idx=int(v[8]), k=int(v[9]))
+        n = hdr["n_ctus"] * hdr["cus_per_ctu"] * hdr["k"]
+        body = np.fromfile(f, dtype=np.uint8)
+    rec = body.reshape(hdr["frames"], 5 * n)
+    shape = (hdr["frames"], hdr["n_ctus"], hdr["cus_per_ctu"], hdr["k"])
+    modes = rec[:, :n].reshape(shape)
+    costs = np.ascontiguousarray(rec[:, n:]).view("<i4").reshape(shape)
+    return hdr, modes, costs
