@@ -1,0 +1,287 @@
+// microbench_tcgen05.cu -- the 4x4 Hadamard SATD on Blackwell's 5th-generation tensor cores (tcgen05.mma, accumulator in
+// TMEM) against the integer routine of the product kernel, inside the same kind of instruction stream.
+//
+// VERDICT r01 asked for this experiment: "stage the 16 differences of 128 blocks as fp16 K-major in SMEM, one tcgen05.mma
+// (M = 128 blocks, K = 16, N = 16, B = H4 (x) H4, fp32 accumulate in TMEM, exact), tcgen05.ld 16 coefficients per lane,
+// sum |.| with the DC rule of kernel_aux_functions.cl:238-246".
+//
+// Formulation measured here (exact for 10-bit samples, no integer->float conversion instruction anywhere):
+//   * a sample s in 0..1023 is the fp16 bit pattern 0x6400 | s (= 1024 + s), two per 32-bit word;
+//   * the A row of a lane is [ original block (16) | predicted block (16) ], K = 32 = two K = 16 MMAs, the second one with
+//     the instruction descriptor's negate-B bit: D = H16 * (1024 + o) - H16 * (1024 + p) = H16 * (o - p) in fp32, the
+//     biases cancel exactly, |coefficient| <= 16 * 1023 is far inside fp32's integer range;
+//   * the product kernel gives every warp its own work (one lane = one (CU, mode)), and a warp can read only its own
+//     quarter of the 128 TMEM lanes.  So each warp issues its OWN M = 128 MMA over the A tile of its group of four warps
+//     (rows of the other three warps are computed too and never read: 4x redundant tensor work, which is free -- the tensor
+//     pipe is idle otherwise) into its own 16 TMEM columns; nothing is synchronised across warps;
+//   * epilogue per lane: tcgen05.ld 32x32b.x16, 15 FADD |c| + DC rule, two F2I.
+//
+// Both variants run the same loop: per block `FILL` independent integer instructions (what the rest of the product kernel
+// does per 4x4 block: interpolation, SAD, boundaries, matrix-vector product -- about 190) and one SATD.  The tensor-core
+// variant is software-pipelined by one block (issue the MMA of block j, do the integer work of block j+1, then read block
+// j's coefficients), single-buffered A rows and TMEM columns.  Reported: ns per (warp, block) per SM-resident warp set,
+// for FILL = 0 and FILL = 190, and bit-exactness of the tensor-core SATD against the integer one.
+//
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/bin/microbench_tcgen05 tools/microbench_tcgen05.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s (line %d)\n", #x, cudaGetErrorString(e_), __LINE__); exit(2); } } while (0)
+
+constexpr int NT = 384, NW = NT / 32;          // like the product kernel: 12 warps, 2 CTAs per SM
+constexpr int A_CHUNK = 128 * 16;              // one K chunk (8 fp16) of 128 rows: 2 KB
+constexpr int A_GROUP = 4 * A_CHUNK;           // K = 32: chunks 0,1 = originals, 2,3 = predictions
+constexpr int SM_A = 0;                        // 3 groups of 4 warps
+constexpr int SM_B = SM_A + (NW / 4) * A_GROUP;   // 16 x 16 fp16, canonical K-major: 512 B
+constexpr int SM_BAR = SM_B + 512;             // one mbarrier per warp
+constexpr int SM_MISC = SM_BAR + NW * 8;
+constexpr int SM_USED = SM_MISC + 16;
+static_assert(SM_USED <= 100 * 1024, "shared memory layout");
+constexpr int SM_PAD = 100 * 1024;             // about what the product kernel occupies, so that exactly 2 CTAs share an SM
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// the product kernel's integer routine (csrc/mip_kernels.cu: satd4x4), e = o - p + 1
+__device__ __forceinline__ int satd4x4_int(const int (&e)[16]) {
+    int m[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int a0 = e[i] + e[12 + i], a1 = e[4 + i] + e[8 + i];
+        int a2 = e[4 + i] - e[8 + i], a3 = e[i] - e[12 + i];
+        m[i] = a0 + a1; m[4 + i] = a2 + a3; m[8 + i] = a0 - a1; m[12 + i] = a3 - a2;
+    }
+    int s = 0, dc = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int b0 = m[4 * r] + m[4 * r + 3], b1 = m[4 * r + 1] + m[4 * r + 2];
+        const int b2 = m[4 * r + 1] - m[4 * r + 2], b3 = m[4 * r] - m[4 * r + 3];
+        if (r == 0) dc = __sad(b0, 16 - b1, 0);
+        else s = __sad(b0, -b1, s);
+        s = __sad(b0, b1, s);
+        s = __sad(b3, -b2, s);
+        s = __sad(b3, b2, s);
+    }
+    return (s + (dc >> 2) + 1) >> 1;
+}
+
+// `fill` independent integer instructions on 8 chains (IMAD / LOP3 / SHF / IADD3 mix: both integer pipes, like the kernel)
+template <int FILL>
+__device__ __forceinline__ void filler(uint32_t (&x)[8]) {
+#pragma unroll
+    for (int i = 0; i < FILL / 8; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if ((i + k) & 1) x[k] = x[k] * 0x9E3779B1u + x[(k + 1) & 7];
+            else x[k] = (x[k] ^ (x[(k + 3) & 7] >> 3)) + 0x7F4A7C15u;
+        }
+    }
+}
+
+// next pair of blocks from the chains: 16 original and 16 predicted samples, 10 bit, as packed pairs
+__device__ __forceinline__ void make_blocks(const uint32_t (&x)[8], uint32_t (&o2)[8], uint32_t (&p2)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        o2[k] = x[k] & 0x03ff03ffu;
+        p2[k] = (x[k] >> 5) & 0x03ff03ffu;
+    }
+}
+
+__device__ __forceinline__ int satd_int_packed(const uint32_t (&o2)[8], const uint32_t (&p2)[8]) {
+    int e[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        e[2 * k] = (int)(o2[k] & 0xffff) - (int)(p2[k] & 0xffff) + 1;
+        e[2 * k + 1] = (int)(o2[k] >> 16) - (int)(p2[k] >> 16) + 1;
+    }
+    return satd4x4_int(e);
+}
+
+template <int FILL>
+__global__ void __launch_bounds__(NT, 2) k_int(int iters, uint32_t seed, int* out) {
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = seed * (k + 1) + (blockIdx.x * NT + threadIdx.x) * 0x85EBCA6Bu + k;
+    int acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        filler<FILL>(x);
+        filler<8>(x);
+        uint32_t o2[8], p2[8];
+        make_blocks(x, o2, p2);
+        acc += satd_int_packed(o2, p2);
+    }
+    out[blockIdx.x * NT + threadIdx.x] = acc;
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    // K-major, no swizzle (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46
+    return (uint64_t)((addr & 0x3ffff) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+template <int FILL>
+__global__ void __launch_bounds__(NT, 2) k_tc(int iters, uint32_t seed, int* out, int* err) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quarter = warp & 3, group = warp >> 2;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + SM_MISC);
+    const uint32_t bar = smem_u32(smem + SM_BAR + warp * 8);
+    // B = H4 (x) H4 as fp16 +-1, canonical K-major: row n at (n % 8) * 16 + (n / 8) * 128, K chunk c at + c * 256
+    if (tid < 256) {
+        const int n = tid >> 4, k = tid & 15;
+        const int h4[4][4] = {{1, 1, 1, 1}, {1, 1, -1, -1}, {1, -1, -1, 1}, {1, -1, 1, -1}};
+        const int v = h4[n >> 2][k >> 2] * h4[n & 3][k & 3];
+        reinterpret_cast<uint16_t*>(smem + SM_B + (n & 7) * 16 + (n >> 3) * 128 + (k >> 3) * 256)[k & 7] = v > 0 ? 0x3c00 : 0xbc00;
+    }
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(s_tmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // B was written through the generic proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t tmem_d = tmem_base + warp * 16;                                   // this warp's 16 accumulator columns
+    const uint32_t tmem_rd = tmem_d + ((uint32_t)(quarter * 32) << 16);               // ... and its quarter of the lanes
+    const uint32_t a_base = smem_u32(smem + SM_A + group * A_GROUP);
+    unsigned char* a_row = smem + SM_A + group * A_GROUP + (quarter * 32 + lane) * 16;   // this lane's 16 bytes in each K chunk
+    const uint64_t desc_ao = smem_desc(a_base, A_CHUNK, 128), desc_ap = smem_desc(a_base + 2 * A_CHUNK, A_CHUNK, 128);
+    const uint64_t desc_b = smem_desc(smem_u32(smem + SM_B), 256, 128);
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = f16 (0), K-major both, N = 16 (2 << 17),
+    // M = 128 (8 << 24); bit 14 negates B
+    const uint32_t idesc = (1u << 4) | (2u << 17) | (8u << 24), idesc_neg = idesc | (1u << 14);
+
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = seed * (k + 1) + (blockIdx.x * NT + threadIdx.x) * 0x85EBCA6Bu + k;
+    int acc = 0;
+    uint32_t parity = 0;
+    bool lost = false;
+    for (int it = 0; it <= iters; ++it) {
+        uint32_t o2[8], p2[8];
+        if (it < iters) {
+            // integer work of block `it`, then its operands: 0x6400 | sample = fp16(1024 + sample), straight into the A rows
+            filler<FILL>(x);
+            filler<8>(x);
+            make_blocks(x, o2, p2);
+        }
+        if (it > 0) {
+            // coefficients of block it - 1
+            int spins = 0;
+            while (!mbar_try_wait(bar, parity)) if (++spins > (1 << 24)) { lost = true; break; }
+            parity ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float c[16];
+            uint32_t r[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(tmem_rd) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 16; ++k) c[k] = __uint_as_float(r[k]);
+            float s = 0.f;
+#pragma unroll
+            for (int k = 1; k < 16; ++k) s += fabsf(c[k]);
+            const int dc = __float2int_rn(fabsf(c[0]));
+            acc += (__float2int_rn(s) + (dc >> 2) + 1) >> 1;
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      // the loads are done before the next MMA overwrites D
+        }
+        if (it < iters) {
+            uint4* d = reinterpret_cast<uint4*>(a_row);
+            d[0 * (A_CHUNK / 16)] = make_uint4(o2[0] | 0x64006400u, o2[1] | 0x64006400u, o2[2] | 0x64006400u, o2[3] | 0x64006400u);
+            d[1 * (A_CHUNK / 16)] = make_uint4(o2[4] | 0x64006400u, o2[5] | 0x64006400u, o2[6] | 0x64006400u, o2[7] | 0x64006400u);
+            d[2 * (A_CHUNK / 16)] = make_uint4(p2[0] | 0x64006400u, p2[1] | 0x64006400u, p2[2] | 0x64006400u, p2[3] | 0x64006400u);
+            d[3 * (A_CHUNK / 16)] = make_uint4(p2[4] | 0x64006400u, p2[5] | 0x64006400u, p2[6] | 0x64006400u, p2[7] | 0x64006400u);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem_d), "l"(desc_ao), "l"(desc_b), "r"(idesc), "r"(0) : "memory");
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem_d), "l"(desc_ap), "l"(desc_b), "r"(idesc_neg), "r"(1) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            }
+            __syncwarp();
+        }
+        if (lost) break;
+    }
+    if (lost) atomicAdd(err, 1);
+    out[blockIdx.x * NT + threadIdx.x] = acc;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+}
+
+template <int FILL>
+static void run(FILE* js, bool first, int sms) {
+    const int grid = sms * 2, n = grid * NT;
+    int *d_a, *d_b, *d_err;
+    CK(cudaMalloc(&d_a, n * sizeof(int))); CK(cudaMalloc(&d_b, n * sizeof(int))); CK(cudaMalloc(&d_err, sizeof(int)));
+    CK(cudaMemset(d_err, 0, sizeof(int)));
+    CK(cudaFuncSetAttribute(k_tc<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_PAD));
+    CK(cudaFuncSetAttribute(k_int<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_PAD));
+    int occ_tc = 0, occ_int = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tc, k_tc<FILL>, NT, SM_PAD));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_int, k_int<FILL>, NT, SM_PAD));
+    // exactness: 64 blocks per lane, every lane its own data
+    k_int<FILL><<<grid, NT, SM_PAD>>>(64, 12345u, d_a);
+    k_tc<FILL><<<grid, NT, SM_PAD>>>(64, 12345u, d_b, d_err);
+    CK(cudaDeviceSynchronize());
+    std::vector<int> a(n), b(n);
+    int err = 0;
+    CK(cudaMemcpy(a.data(), d_a, n * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b.data(), d_b, n * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    long bad = 0;
+    for (int i = 0; i < n; ++i) bad += a[i] != b[i];
+    // timing
+    const int iters = 2000;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float ms_int = 1e9f, ms_tc = 1e9f;
+    for (int rep = 0; rep < 3; ++rep) {
+        float ms;
+        CK(cudaEventRecord(e0)); k_int<FILL><<<grid, NT, SM_PAD>>>(iters, 777u + rep, d_a); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < ms_int) ms_int = ms;
+        CK(cudaEventRecord(e0)); k_tc<FILL><<<grid, NT, SM_PAD>>>(iters, 777u + rep, d_b, d_err); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < ms_tc) ms_tc = ms;
+    }
+    CK(cudaGetLastError());
+    // per SM: 24 warps, `iters` blocks each
+    const double clk = 1.965e9;
+    const double cyc_int = ms_int * 1e-3 * clk / iters / (2.0 * NW), cyc_tc = ms_tc * 1e-3 * clk / iters / (2.0 * NW);
+    fprintf(js, "%s\n {\"fill_instructions_per_block\": %d, \"ctas_per_sm\": [%d, %d], \"lanes_checked\": %d, \"satd_mismatches\": %ld, \"lost_barriers\": %d, "
+                "\"ms_int\": %.4f, \"ms_tc\": %.4f, \"sm_cycles_per_warp_block_int\": %.2f, \"sm_cycles_per_warp_block_tc\": %.2f, \"tc_over_int\": %.3f}",
+            first ? "" : ",", FILL, occ_int, occ_tc, n, bad, err, ms_int, ms_tc, cyc_int, cyc_tc, ms_tc / ms_int);
+    printf("FILL %3d: exact %s (%ld mismatches of %d lanes x 64 blocks, %d lost barriers); int %.3f ms, tcgen05 %.3f ms -> %.2f vs %.2f SM cycles per (warp, block), ratio %.3f\n",
+           FILL, bad == 0 && err == 0 ? "yes" : "NO", bad, n, err, ms_int, ms_tc, cyc_int, cyc_tc, ms_tc / ms_int);
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_err);
+}
+
+int main(int argc, char** argv) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    FILE* js = fopen(argc > 1 ? argv[1] : "/dev/null", "w");
+    fprintf(js, "{\"device\": \"%s\", \"sms\": %d, \"what\": \"4x4 Hadamard SATD per lane-block: integer routine of the product kernel vs tcgen05.mma "
+                "(fp16 [orig|pred] rows, K = 32, negate-B, one M = 128 MMA pair per warp and block, accumulator in TMEM, tcgen05.ld epilogue), "
+                "inside a stream of `fill` independent integer instructions per block; 384 threads, 2 CTAs per SM\", \"runs\": [", prop.name, prop.multiProcessorCount);
+    run<0>(js, true, prop.multiProcessorCount);
+    run<96>(js, false, prop.multiProcessorCount);
+    run<184>(js, false, prop.multiProcessorCount);
+    fprintf(js, "\n]}\n");
+    fclose(js);
+    return 0;
+}

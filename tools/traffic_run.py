@@ -1,0 +1,42 @@
+#!/usr/bin/env python3
+"""Steady-state DRAM traffic of the fused cost kernel: N launches in the bench configuration (filter 8 / k 2, costs +
+decisions), frames from a 32-frame pool, three rotating 52.8 MB cost tables -- more than the 126 MB L2 holds -- between
+cudaProfilerStart/Stop, after 9 identical warm-up launches (so the L2 holds as much dirty data of earlier launches when
+the range opens as it keeps back when the range closes).  Run under
+  ncu --replay-mode range --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum ...
+and divide by N.  Usage: traffic_run.py [launches]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "vvc-mip-gpu_b200"))
+import numpy as np
+import torch
+
+import mipb200
+from mipb200 import frames
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+W, H, B = 1920, 1080, 32
+eng = mipb200.Engine(W, H, filter_type=8, kernel_idx=2, slots=1, emit=mipb200.EMIT_DECISIONS)
+base = [frames.natural_frame(W, H, i) for i in range(4)]
+pool = torch.from_numpy(np.stack([np.roll(base[i % 4], 8 * (i // 4), axis=1) for i in range(B)]).view(np.int16)).cuda()
+cost = torch.empty((3, eng.n_ctus, mipb200.COSTS_PER_CTU), dtype=torch.int32, device="cuda")
+bm = torch.empty((3, eng.n_ctus, mipb200.CUS_PER_CTU), dtype=torch.uint8, device="cuda")
+bc = torch.empty((3, eng.n_ctus, mipb200.CUS_PER_CTU), dtype=torch.int32, device="cuda")
+st = torch.cuda.current_stream().cuda_stream
+
+
+def go(i):
+    eng.run_device(pool[i % B].data_ptr(), cost[i % 3].data_ptr(), d_best_mode=bm[i % 3].data_ptr(), d_best_cost=bc[i % 3].data_ptr(), stream=st)
+
+
+for i in range(9):
+    go(i)
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+for i in range(9, 9 + n):
+    go(i)
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print(f"{n} launches in the profiled range; checksum {int(cost[0].to(torch.int64).clamp(min=0).sum())}")

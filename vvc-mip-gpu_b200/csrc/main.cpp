@@ -13,7 +13,7 @@
 //
 // Memory model.  The reference reads every frame into one array and keeps every frame's table (main.cpp:364-384,
 // :656-662); that is 250 GB for BASELINE config 5 (2048 frames of 7680x4320).  Here frames live in a bounded,
-// page-locked RING (--RingFrames, default: 2 GiB worth, at least 4 per GPU) that the engines DMA from in place.  When
+// page-locked RING (--RingFrames, default: 2 GiB worth, at least Slots + 1 per GPU) that the engines DMA from in place.  When
 // the input fits the ring it is loaded before the timed window, exactly like the reference; otherwise a reader thread
 // streams it (the ring is full when the window opens, slots are refilled as their frames are collected).  Results are
 // consumed frame by frame as they are collected -- written to their place in the binary logs (pwrite), hashed into the
@@ -75,7 +75,8 @@ struct Options {
     int bitDepth = 10;
     int stageStamps = -1;   // -1: follow TRACE_POWER when one GPU is used
     int inputFrames = 0;    // frames the input file holds (0: as many as -f); frame poc is file frame poc % inputFrames
-    int ringFrames = 0;     // capacity of the page-locked frame ring (0: 2 GiB worth, at least 4 per GPU)
+    int ringFrames = 0;     // capacity of the page-locked frame ring (0: 2 GiB worth, at least Slots + 1 per GPU)
+    int slots = 3;          // frames in flight per engine
     std::string inputFormat = "csv", decisionsLog, binaryLog, decisionsBin, digest;
     bool allFrames = false, compat = false, noLog = false, help = false, energy = false;
 };
@@ -83,9 +84,9 @@ struct Options {
 const char* kLongOpts[] = {"help", "DeviceIndex", "FramesToBeEncoded", "Resolution", "OriginalFrames", "OutputPreffix",
                            "FilterType", "KernelIdx", "UseAlternativeSamples", "NumGpus", "AllFrames", "Compat", "NoLog",
                            "InputFormat", "DecisionsLog", "TopK", "Energy", "StageStamps", "BitDepth", "BinaryLog", "DecisionsBin", "Digest",
-                           "InputFrames", "RingFrames"};
+                           "InputFrames", "RingFrames", "Slots"};
 const bool kTakesValue[] = {false, true, true, true, true, true, true, true, true, true, false, false, false, true, true,
-                            true, false, true, true, true, true, true, true, true};
+                            true, false, true, true, true, true, true, true, true, true};
 constexpr int kNumOpts = sizeof(kLongOpts) / sizeof(kLongOpts[0]);
 
 void print_help() {
@@ -107,7 +108,8 @@ void print_help() {
            "  --DecisionsBin arg             write every frame's decisions raw: uint8 modes then int32 costs (64-byte header)\n"
            "  --Digest arg                   write POC,<64-bit hash of each result array> for every frame\n"
            "  --InputFrames arg              frames held by the input file; frame poc reads file frame poc %% arg (default: -f)\n"
-           "  --RingFrames arg               capacity of the page-locked frame ring (default: 2 GiB worth, >= 4 per GPU)\n"
+           "  --RingFrames arg               capacity of the page-locked frame ring (default: 2 GiB worth, >= Slots + 1 per GPU)\n"
+           "  --Slots arg (=3)               frames in flight per GPU (upload, kernels and read-back of different frames overlap)\n"
            "  --TopK arg (=1)                with --DecisionsLog: the k cheapest modes per CU (adds Mode2,Cost2,... columns)\n"
            "  --Energy                       report joules per frame from the board's NVML energy counter\n"
            "  --BitDepth arg (=10)           8 | 10 | 12; 10 is the reference's pipeline (also for 8-bit content taken as is)\n"
@@ -193,6 +195,7 @@ bool parse_args(int argc, char** argv, Options& o) {
             case 21: o.digest = val; break;
             case 22: ok = to_int(val, &o.inputFrames); break;
             case 23: ok = to_int(val, &o.ringFrames); break;
+            case 24: ok = to_int(val, &o.slots); break;
         }
         if (!ok) { fprintf(stderr, "the argument ('%s') for option '--%s' is invalid\n", val.c_str(), kLongOpts[opt]); return false; }
     }
@@ -364,24 +367,54 @@ struct FrameRing {
     void fail() { std::lock_guard<std::mutex> lk(mu); failed = true; cv.notify_all(); }
 };
 
-// 64-bit digest of a result array (4 interleaved multiply-rotate lanes over 64-bit words, then a fold): fast enough to
-// run inside the collect loop (several GB/s per host thread) and sensitive to any changed, moved or missing word.
-uint64_t digest64(const void* data, size_t bytes) {
+// 64-bit digest of a result array, sensitive to any changed, moved or missing word.  Eight accumulator lanes over 64-byte
+// stripes (acc[i] += lo32(w ^ k) * hi32(w ^ k); acc[i ^ 1] += w: compiles to packed 32x32->64 multiplies), scrambled every
+// 64 KiB.  Arrays are hashed in fixed 4 MiB segments and the digest is the digest of the segment digests, so large arrays
+// (55 MB of decisions per 4320p frame, 7.7 GB/s per GPU) can be hashed by a few threads with the same result as by one.
+uint64_t digest64_segment(const void* data, size_t bytes) {
+    static const uint64_t K[8] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull,
+                                  0xFF51AFD7ED558CCDull, 0xC4CEB9FE1A85EC53ull, 0x2545F4914F6CDD1Dull, 0x94D049BB133111EBull};
     const uint8_t* p = static_cast<const uint8_t*>(data);
-    uint64_t h[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
-    const uint64_t m0 = 0xFF51AFD7ED558CCDull, m1 = 0xC4CEB9FE1A85EC53ull;
-    size_t n = bytes / 32;
-    for (size_t i = 0; i < n; ++i, p += 32) {
-        uint64_t w[4];
-        memcpy(w, p, 32);
-        for (int k = 0; k < 4; ++k) { h[k] = (h[k] ^ w[k]) * m0; h[k] = (h[k] << 29) | (h[k] >> 35); }
+    uint64_t acc[8];
+    for (int i = 0; i < 8; ++i) acc[i] = K[7 - i];
+    const size_t stripes = bytes / 64;
+    for (size_t s = 0; s < stripes; ++s, p += 64) {
+        uint64_t w[8];
+        memcpy(w, p, 64);
+        for (int i = 0; i < 8; ++i) {
+            const uint64_t d = w[i] ^ K[i];
+            acc[i] += (d & 0xffffffffu) * (d >> 32);
+            acc[i ^ 1] += w[i];
+        }
+        if ((s & 1023) == 1023)
+            for (int i = 0; i < 8; ++i) acc[i] = (acc[i] ^ (acc[i] >> 47) ^ K[i]) * 0x9E3779B1ull;
     }
-    uint64_t tail[4] = {0, 0, 0, 0};
-    memcpy(tail, p, bytes % 32);
-    for (int k = 0; k < 4; ++k) { h[k] = (h[k] ^ tail[k]) * m0; h[k] = (h[k] << 29) | (h[k] >> 35); }
-    uint64_t r = bytes;
-    for (int k = 0; k < 4; ++k) { r = (r ^ h[k]) * m1; r ^= r >> 32; }
+    uint64_t tail[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    memcpy(tail, p, bytes % 64);
+    for (int i = 0; i < 8; ++i) { const uint64_t d = tail[i] ^ K[i]; acc[i] += (d & 0xffffffffu) * (d >> 32); acc[i ^ 1] += tail[i]; }
+    uint64_t r = bytes * 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < 8; ++i) { r = (r ^ acc[i]) * 0xFF51AFD7ED558CCDull; r ^= r >> 29; }
     return r;
+}
+
+uint64_t digest64(const void* data, size_t bytes, int maxThreads = 4) {
+    constexpr size_t SEG = (size_t)4 << 20;
+    const size_t nseg = (bytes + SEG - 1) / SEG;
+    std::vector<uint64_t> part(nseg ? nseg : 1, 0);
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    auto seg = [&](size_t i) { part[i] = digest64_segment(p + i * SEG, std::min(SEG, bytes - i * SEG)); };
+    const int nth = (int)std::min<size_t>(maxThreads, nseg);
+    if (nth <= 1) {
+        for (size_t i = 0; i < nseg; ++i) seg(i);
+    } else {
+        std::atomic<size_t> next{0};
+        auto work = [&] { for (size_t i; (i = next.fetch_add(1)) < nseg;) seg(i); };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nth; ++t) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+    }
+    return digest64_segment(part.data(), part.size() * sizeof(uint64_t)) ^ (uint64_t)bytes;
 }
 
 // ---- cost log (main_aux_functions.h:735-798)
@@ -532,7 +565,7 @@ mipb200_engine* create_engine(Shared* sh, int g, mipb200_config* cfg_out) {
     const Options& o = sh->opt;
     mipb200_config cfg;
     cfg.width = sh->W; cfg.height = sh->H; cfg.device = o.deviceIndex + g;
-    cfg.filter_type = sh->filterType; cfg.kernel_idx = o.kernelIdx; cfg.slots = 3;
+    cfg.filter_type = sh->filterType; cfg.kernel_idx = o.kernelIdx; cfg.slots = o.slots;
     cfg.top_k = o.topK > 1 ? o.topK : 0;
     cfg.bit_depth = o.bitDepth;
     cfg.emit = sh->emit;
@@ -699,6 +732,7 @@ int main(int argc, char** argv) {
     if (o.topK < 0 || o.topK > MIPB200_TOPK_MAX) { printf("  [!] ERROR: TopK must be in 1..%d\n", MIPB200_TOPK_MAX); return 1; }
     if (o.bitDepth != 8 && o.bitDepth != 10 && o.bitDepth != 12) { printf("  [!] ERROR: BitDepth must be 8, 10 or 12\n"); return 1; }
     if (o.topK > 1 && o.decisionsLog.empty() && o.decisionsBin.empty()) { printf("  [!] ERROR: TopK needs --DecisionsLog\n"); return 1; }
+    if (o.slots < 1 || o.slots > 16) { printf("  [!] ERROR: Slots must be in 1..16\n"); return 1; }
     if (o.inputFrames < 0 || o.ringFrames < 0) { printf("  [!] ERROR: InputFrames and RingFrames must be positive\n"); return 1; }
     if (o.inputFormat != "csv" && o.inputFormat != "u16" && o.inputFormat != "yuv420p" && o.inputFormat != "yuv420p10le") {
         printf("  [!] ERROR: InputFormat %s not supported (csv, u16, yuv420p, yuv420p10le)\n", o.inputFormat.c_str());
@@ -719,8 +753,9 @@ int main(int argc, char** argv) {
     ring.period = o.inputFrames > 0 ? std::min(o.inputFrames, o.nFrames) : o.nFrames;
     {
         const size_t frameBytes = ring.fpx * sizeof(uint16_t);
-        long cap = o.ringFrames > 0 ? o.ringFrames : (long)std::max<size_t>((size_t)4 * o.numGpus, ((size_t)2 << 30) / frameBytes);
-        cap = std::max<long>(cap, 4L * o.numGpus);
+        const long perGpu = o.slots + 1;   // frames in flight per engine plus one being read: the reader stays ahead
+        long cap = o.ringFrames > 0 ? o.ringFrames : (long)std::max<size_t>((size_t)perGpu * o.numGpus, ((size_t)2 << 30) / frameBytes);
+        cap = std::max<long>(cap, perGpu * o.numGpus);
         ring.resident = ring.period <= cap;
         ring.capacity = (int)(ring.resident ? ring.period : cap);
         void* mem = nullptr;

@@ -137,6 +137,7 @@ struct Ctx {
     const uint16_t* s_refL;   // column slots: sample (slot, y) at slot * RL_STRIDE + 8 + y
     const uint16_t* s_dc;     // one cell holding 1 << (bitDepth - 1)
     int maxv;                 // (1 << bitDepth) - 1
+    uint32_t maxv2;           // maxv in both 16-bit halves
     uint32_t* s_red;          // this thread's column of the [RED_WORDS][NT] scratch
     const uint8_t* s_mat;
     int ctuX, tileY;          // frame position of the tile origin
@@ -326,7 +327,12 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
     const bool tr = mode >= M;
     const int mat = tr ? mode - M : mode;
     const int first = bd[0];
-    const int acc0 = 32 + 64 * first;      // ((32 + sum) >> 6) + first == (32 + 64 * first + sum) >> 6   (intra.cl:454, 481)
+    // ((32 + sum) >> 6) + first == (32 + 64 * first + sum) >> 6   (intra.cl:454, 481).  For sizeId 1 and 2 everything is
+    // carried 4x (inputs and start value): (4 * acc) >> 8 == acc >> 6, and a shift by 8 is a byte selection, so one PRMT
+    // both shifts and packs two samples and one VIMNMX.S16x2.RELU clamps both (the 16-bit range holds: kernels_init checks
+    // the matrices' row sums).
+    constexpr int SC = SID == 0 ? 0 : 2;
+    const int acc0 = (32 + 64 * first) << SC;
     int ipk[B];
     {
         int in[2 * B];
@@ -334,7 +340,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 #pragma unroll
         for (int i = 1; i < 2 * B; ++i) in[i] = bd[i] - first;
 #pragma unroll
-        for (int k = 0; k < B; ++k) ipk[k] = (in[2 * k] & 0xffff) | (in[2 * k + 1] << 16);
+        for (int k = 0; k < B; ++k) ipk[k] = ((in[2 * k] << SC) & 0xffff) | (in[2 * k + 1] << (16 + SC));
     }
 
     if constexpr (SID == 0) {
@@ -378,8 +384,8 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
                 acc = __dp2a_hi(ipk[1], cw.x, acc);  acd = __dp2a_hi(ipk[1], cw.z, acd);
                 acc = __dp2a_lo(ipk[2], cw.y, acc);  acd = __dp2a_lo(ipk[2], cw.w, acd);
                 acc = __dp2a_hi(ipk[3], cw.y, acc);  acd = __dp2a_hi(ipk[3], cw.w, acd);
-                const uint32_t v0 = (uint32_t)clamp_px(acc >> 6, c.maxv), v1 = (uint32_t)clamp_px(acd >> 6, c.maxv);
-                *reinterpret_cast<uint32_t*>(wp + (b >> 1) * RED_WB) = __byte_perm(v0, v1, 0x5410);   // v0 | v1 << 16
+                // bytes 1..2 of each accumulator = (4 * acc) >> 8 as a signed 16-bit value; clamp both halves to 0..maxv at once
+                *reinterpret_cast<uint32_t*>(wp + (b >> 1) * RED_WB) = __vimin_s16x2_relu(__byte_perm(acc, acd, 0x6521), c.maxv2);
             }
             mp += R * 8;
             wp += RED_ROWB<R>;
@@ -679,6 +685,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     c.s_refL = s_refL;
     c.s_dc = s_dc;
     c.maxv = maxv;
+    c.maxv2 = (uint32_t)maxv * 0x10001u;
     c.s_red = s_red + tid;
     c.s_mat = s_mat;
     c.ctuX = ctuX;
@@ -1009,6 +1016,15 @@ cudaError_t kernels_init(int chunks, const double* weights) {
                 mat[M0_OFF + m * M0_STRIDE + p * 4 + i] = v;
                 mat[M0T_OFF + m * M0_STRIDE + tpos(p, 4) * 4 + i] = v;
             }
+    {   // the packed clamp of run_task() keeps (sum >> 6) + first in a signed 16-bit half: true for every bit depth up to 12
+        // iff maxv * (largest row sum of |coef - 32|) / 64 + maxv + 1 < 32768, and the 4x accumulator stays far inside int32
+        int worst = 0;
+        for (int m = 0; m < 6; ++m)
+            for (int p = 0; p < 64; ++p) { int t = 0; for (int i = 1; i < 8; ++i) t += abs(mip_mat_id2(m, p, i) - 32); worst = std::max(worst, t); }
+        for (int m = 0; m < 8; ++m)
+            for (int p = 0; p < 16; ++p) { int t = 0; for (int i = 0; i < 8; ++i) t += abs(mip_mat_id1(m, p, i) - 32); worst = std::max(worst, t); }
+        if ((4095 * worst + 32) / 64 + 4096 >= 32768) return cudaErrorInvalidValue;
+    }
     if ((err = cudaMemcpyToSymbol(g_mat, mat.data(), MAT_BYTES)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(mip_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(mip_cost_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return err;
