@@ -33,7 +33,12 @@
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s (line %d)\n", #x, cudaGetErrorString(e_), __LINE__); exit(2); } } while (0)
 
-constexpr int NT = 384, NW = NT / 32;          // like the product kernel: 12 warps, 2 CTAs per SM
+#ifndef MB_NT
+#define MB_NT 384
+#endif
+constexpr int NT = MB_NT, NW = NT / 32;        // 384: like the product kernel, 12 warps, 2 CTAs per SM; 256: 8 warps, 3 CTAs per SM
+constexpr int CTAS = NT == 768 ? 1 : NT == 384 ? 2 : 3;   // 24 warps per SM in every variant
+constexpr int TMEM_COLS = NW * 16 <= 128 ? 128 : NW * 16 <= 256 ? 256 : 512;   // 16 accumulator columns per warp, allocations are powers of two
 constexpr int A_CHUNK = 128 * 16;              // one K chunk (8 fp16) of 128 rows: 2 KB
 constexpr int A_GROUP = 4 * A_CHUNK;           // K = 32: chunks 0,1 = originals, 2,3 = predictions
 constexpr int SM_A = 0;                        // 3 groups of 4 warps
@@ -41,8 +46,8 @@ constexpr int SM_B = SM_A + (NW / 4) * A_GROUP;   // 16 x 16 fp16, canonical K-m
 constexpr int SM_BAR = SM_B + 512;             // one mbarrier per warp
 constexpr int SM_MISC = SM_BAR + NW * 8;
 constexpr int SM_USED = SM_MISC + 16;
-static_assert(SM_USED <= 100 * 1024, "shared memory layout");
-constexpr int SM_PAD = 100 * 1024;             // about what the product kernel occupies, so that exactly 2 CTAs share an SM
+constexpr int SM_PAD = NT == 768 ? 200 * 1024 : NT == 384 ? 100 * 1024 : 72 * 1024;   // so that exactly CTAS CTAs share an SM
+static_assert(SM_USED <= SM_PAD, "shared memory layout");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -101,8 +106,26 @@ __device__ __forceinline__ int satd_int_packed(const uint32_t (&o2)[8], const ui
     return satd4x4_int(e);
 }
 
+// how many CTAs of a kernel really share an SM (the occupancy calculator reports 1 for every kernel that allocates TMEM)
+__device__ int g_resident[256], g_resident_max;
+__device__ __forceinline__ void residency_enter() {
+    if (threadIdx.x == 0) {
+        uint32_t sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        atomicMax(&g_resident_max, atomicAdd(&g_resident[sm], 1) + 1);
+    }
+}
+__device__ __forceinline__ void residency_leave() {
+    if (threadIdx.x == 0) {
+        uint32_t sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        atomicSub(&g_resident[sm], 1);
+    }
+}
+
 template <int FILL>
-__global__ void __launch_bounds__(NT, 2) k_int(int iters, uint32_t seed, int* out) {
+__global__ void __launch_bounds__(NT, CTAS) k_int(int iters, uint32_t seed, int* out) {
+    residency_enter();
     uint32_t x[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = seed * (k + 1) + (blockIdx.x * NT + threadIdx.x) * 0x85EBCA6Bu + k;
@@ -115,6 +138,7 @@ __global__ void __launch_bounds__(NT, 2) k_int(int iters, uint32_t seed, int* ou
         acc += satd_int_packed(o2, p2);
     }
     out[blockIdx.x * NT + threadIdx.x] = acc;
+    residency_leave();
 }
 
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
@@ -129,8 +153,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
 }
 
 template <int FILL>
-__global__ void __launch_bounds__(NT, 2) k_tc(int iters, uint32_t seed, int* out, int* err) {
+__global__ void __launch_bounds__(NT, CTAS) k_tc(int iters, uint32_t seed, int* out, int* err) {
     extern __shared__ __align__(128) unsigned char smem[];
+    residency_enter();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quarter = warp & 3, group = warp >> 2;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + SM_MISC);
     const uint32_t bar = smem_u32(smem + SM_BAR + warp * 8);
@@ -143,7 +168,7 @@ __global__ void __launch_bounds__(NT, 2) k_tc(int iters, uint32_t seed, int* out
     }
     if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(s_tmem)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -222,12 +247,13 @@ __global__ void __launch_bounds__(NT, 2) k_tc(int iters, uint32_t seed, int* out
     out[blockIdx.x * NT + threadIdx.x] = acc;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    residency_leave();
 }
 
 template <int FILL>
 static void run(FILE* js, bool first, int sms) {
-    const int grid = sms * 2, n = grid * NT;
+    const int grid = sms * CTAS, n = grid * NT;
     int *d_a, *d_b, *d_err;
     CK(cudaMalloc(&d_a, n * sizeof(int))); CK(cudaMalloc(&d_b, n * sizeof(int))); CK(cudaMalloc(&d_err, sizeof(int)));
     CK(cudaMemset(d_err, 0, sizeof(int)));
@@ -252,22 +278,28 @@ static void run(FILE* js, bool first, int sms) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     float ms_int = 1e9f, ms_tc = 1e9f;
+    int res_int = 0, res_tc = 0;
+    const int zero = 0;
     for (int rep = 0; rep < 3; ++rep) {
         float ms;
+        CK(cudaMemcpyToSymbol(g_resident_max, &zero, sizeof(int)));
         CK(cudaEventRecord(e0)); k_int<FILL><<<grid, NT, SM_PAD>>>(iters, 777u + rep, d_a); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < ms_int) ms_int = ms;
+        CK(cudaMemcpyFromSymbol(&res_int, g_resident_max, sizeof(int)));
+        CK(cudaMemcpyToSymbol(g_resident_max, &zero, sizeof(int)));
         CK(cudaEventRecord(e0)); k_tc<FILL><<<grid, NT, SM_PAD>>>(iters, 777u + rep, d_b, d_err); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < ms_tc) ms_tc = ms;
+        CK(cudaMemcpyFromSymbol(&res_tc, g_resident_max, sizeof(int)));
     }
     CK(cudaGetLastError());
     // per SM: 24 warps, `iters` blocks each
     const double clk = 1.965e9;
-    const double cyc_int = ms_int * 1e-3 * clk / iters / (2.0 * NW), cyc_tc = ms_tc * 1e-3 * clk / iters / (2.0 * NW);
-    fprintf(js, "%s\n {\"fill_instructions_per_block\": %d, \"ctas_per_sm\": [%d, %d], \"lanes_checked\": %d, \"satd_mismatches\": %ld, \"lost_barriers\": %d, "
+    const double cyc_int = ms_int * 1e-3 * clk / iters / (double)(CTAS * NW), cyc_tc = ms_tc * 1e-3 * clk / iters / (double)(CTAS * NW);
+    fprintf(js, "%s\n {\"fill_statements_per_block\": %d, \"ctas_per_sm_occupancy_api\": [%d, %d], \"ctas_per_sm_measured\": [%d, %d], \"lanes_checked\": %d, \"satd_mismatches\": %ld, \"lost_barriers\": %d, "
                 "\"ms_int\": %.4f, \"ms_tc\": %.4f, \"sm_cycles_per_warp_block_int\": %.2f, \"sm_cycles_per_warp_block_tc\": %.2f, \"tc_over_int\": %.3f}",
-            first ? "" : ",", FILL, occ_int, occ_tc, n, bad, err, ms_int, ms_tc, cyc_int, cyc_tc, ms_tc / ms_int);
-    printf("FILL %3d: exact %s (%ld mismatches of %d lanes x 64 blocks, %d lost barriers); int %.3f ms, tcgen05 %.3f ms -> %.2f vs %.2f SM cycles per (warp, block), ratio %.3f\n",
-           FILL, bad == 0 && err == 0 ? "yes" : "NO", bad, n, err, ms_int, ms_tc, cyc_int, cyc_tc, ms_tc / ms_int);
+            first ? "" : ",", FILL, occ_int, occ_tc, res_int, res_tc, n, bad, err, ms_int, ms_tc, cyc_int, cyc_tc, ms_tc / ms_int);
+    printf("NT %d, CTAs/SM (api) int %d tc %d (measured) int %d tc %d, FILL %3d: exact %s (%ld mismatches of %d lanes x 64 blocks, %d lost barriers); int %.3f ms, tcgen05 %.3f ms -> %.2f vs %.2f SM cycles per (warp, block), ratio %.3f\n",
+           NT, occ_int, occ_tc, res_int, res_tc, FILL, bad == 0 && err == 0 ? "yes" : "NO", bad, n, err, ms_int, ms_tc, cyc_int, cyc_tc, ms_tc / ms_int);
     cudaFree(d_a); cudaFree(d_b); cudaFree(d_err);
 }
 
@@ -277,7 +309,7 @@ int main(int argc, char** argv) {
     FILE* js = fopen(argc > 1 ? argv[1] : "/dev/null", "w");
     fprintf(js, "{\"device\": \"%s\", \"sms\": %d, \"what\": \"4x4 Hadamard SATD per lane-block: integer routine of the product kernel vs tcgen05.mma "
                 "(fp16 [orig|pred] rows, K = 32, negate-B, one M = 128 MMA pair per warp and block, accumulator in TMEM, tcgen05.ld epilogue), "
-                "inside a stream of `fill` independent integer instructions per block; 384 threads, 2 CTAs per SM\", \"runs\": [", prop.name, prop.multiProcessorCount);
+                "inside a stream of `fill` independent integer instructions per block; %d threads per CTA, %d CTAs per SM wanted, %d TMEM columns per CTA\", \"runs\": [", prop.name, prop.multiProcessorCount, NT, CTAS, TMEM_COLS);
     run<0>(js, true, prop.multiProcessorCount);
     run<96>(js, false, prop.multiProcessorCount);
     run<184>(js, false, prop.multiProcessorCount);

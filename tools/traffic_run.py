@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Steady-state DRAM traffic of the fused cost kernel: N launches in the bench configuration (filter 8 / k 2, costs +
 decisions), frames from a 32-frame pool, three rotating 52.8 MB cost tables -- more than the 126 MB L2 holds -- between
-cudaProfilerStart/Stop, after 9 identical warm-up launches (so the L2 holds as much dirty data of earlier launches when
+cudaProfilerStart/Stop, after 36 identical warm-up launches (every frame's tensor map is encoded and cached by then --
+range replay refuses driver calls such as cuTensorMapEncodeTiled inside the range -- and the L2 holds as much dirty data of earlier launches when
 the range opens as it keeps back when the range closes).  Run under
   ncu --replay-mode range --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum ...
 and divide by N.  Usage: traffic_run.py [launches]"""
@@ -31,11 +32,11 @@ def go(i):
     eng.run_device(pool[i % B].data_ptr(), cost[i % 3].data_ptr(), d_best_mode=bm[i % 3].data_ptr(), d_best_cost=bc[i % 3].data_ptr(), stream=st)
 
 
-for i in range(9):
+for i in range(36):
     go(i)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
-for i in range(9, 9 + n):
+for i in range(36, 36 + n):
     go(i)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()

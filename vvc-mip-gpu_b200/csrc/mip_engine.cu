@@ -111,6 +111,9 @@ struct mipb200_engine {
     // frames (measured: 850 frames/s with full tables at 1080p; in order: the link rate with the same 3 slots).
     cudaStream_t d2h_stream = nullptr;
     mipb200::FilterParams fp;         // fused low-pass filter of this configuration
+    // The kernel's CTAs are persistent and take their work from a few words in global memory that the kernel itself
+    // leaves zeroed: launches that share them must not overlap, so there is one set per stream the engine launches on.
+    std::vector<std::pair<cudaStream_t, int*>> sched;
     FILE* trace = nullptr;            // MIPB200_TRACE=<file>: per-frame device timeline (debugging aid, not API)
     cudaEvent_t ev_base = nullptr;
 };
@@ -182,6 +185,7 @@ MIPB200_API void mipb200_destroy(mipb200_engine* e) {
     for (auto& s : e->slots) free_slot(s);
     if (e->d2h_stream) { cudaStreamSynchronize(e->d2h_stream); cudaStreamDestroy(e->d2h_stream); }
     if (e->aux_stream) { cudaStreamSynchronize(e->aux_stream); cudaStreamDestroy(e->aux_stream); }
+    for (auto& p : e->sched) cudaFree(p.second);
     if (e->ev_base) cudaEventDestroy(e->ev_base);
     if (e->trace) fclose(e->trace);
     delete e;
@@ -203,10 +207,10 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
     {
         std::lock_guard<std::mutex> lk(g_init_mutex);
         if (!g_dev_init[cfg->device]) {
-            // chunks per CTU half (= CTAs per half): 3 equal shares are the throughput optimum with frames overlapping on the
-            // slot streams (0.444 vs 0.454 ms with 4; a lone frame prefers 4: 0.485 vs 0.522 ms).  Tuning knobs, not API:
-            // MIPB200_CHUNKS=n (equal shares), MIPB200_CHUNK_WEIGHTS=a,b,c,.. (relative cost shares in launch order).
-            int chunks = 3;
+            // own units per CTU half: the 12-mode half of a half's work is cut into that many pieces (the other half, the
+            // tail, is shared task by task; see mip_cost_kernel).  Tuning knobs, not API: MIPB200_CHUNKS=n (equal shares),
+            // MIPB200_CHUNK_WEIGHTS=a,b,.. (relative cost shares).
+            int chunks = 2;
             double weights[64];
             bool haveW = false;
             if (const char* ew = getenv("MIPB200_CHUNK_WEIGHTS")) {
@@ -223,12 +227,8 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
             } else if (const char* ev = getenv("MIPB200_CHUNKS")) {
                 chunks = atoi(ev);
             }
-            if (chunks < 2 || chunks > 64)
-                return fail(MIPB200_EINVAL, "%d chunks per CTU half: need 2..64 (one chunk would hold more CUs than the kernel's decision table)", chunks);
-            const cudaError_t ke = mipb200::kernels_init(chunks, haveW ? weights : nullptr);
-            if (ke == cudaErrorInvalidValue)
-                return fail(MIPB200_EINVAL, "this split into %d chunks puts more than 2048 CUs into one chunk; use more chunks or more even weights", chunks);
-            CU_TRY(ke);
+            if (chunks < 1 || chunks > 64) return fail(MIPB200_EINVAL, "%d own units per CTU half: need 1..64", chunks);
+            CU_TRY(mipb200::kernels_init(chunks, haveW ? weights : nullptr));
             g_dev_init[cfg->device] = true;
         }
     }
@@ -326,7 +326,14 @@ MIPB200_API uint16_t* mipb200_next_input(mipb200_engine* e) {
 static int enqueue_kernels(mipb200_engine* e, const uint16_t* d_frame, int32_t* d_cost, int32_t* d_sad,
                            int32_t* d_satd, uint8_t* d_bm, int32_t* d_bc, cudaStream_t st) {
     const mipb200_config& c = e->cfg;
-    CU_TRY(mipb200::launch_costs(d_frame, c.width, c.height, c.bit_depth, e->fp, d_cost, d_sad, d_satd, d_bm, d_bc, st));
+    int* sch = nullptr;
+    for (auto& p : e->sched)
+        if (p.first == st) { sch = p.second; break; }
+    if (!sch) {
+        CU_TRY(mipb200::sched_alloc(c.width, c.height, &sch));
+        e->sched.emplace_back(st, sch);
+    }
+    CU_TRY(mipb200::launch_costs(d_frame, c.width, c.height, c.bit_depth, e->fp, d_cost, d_sad, d_satd, d_bm, d_bc, sch, st));
     e->launches++;
     return MIPB200_OK;
 }
