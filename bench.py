@@ -273,9 +273,11 @@ class Workload:
         return ms, launches
 
     def kernel_alone(self, reps):
-        """the fused kernel of THIS configuration (filter, costs + decisions) back to back on one stream -> ms per launch"""
+        """the fused kernel of THIS configuration (filter, costs + decisions), one frame at a time: launches back to back on
+        one stream, the engine told that nothing overlaps (MIPB200_LAUNCH_LATENCY) -> ms per launch"""
         torch, mip = self.torch, self.mip
         eng = self.engine(1, mip.EMIT_DECISIONS)
+        eng.set_launch_mode(mip.LAUNCH_LATENCY)      # one frame at a time on the GPU: the split the engine uses for a lone frame
         sp = self.streams[0].cuda_stream
 
         def go(i):
@@ -485,7 +487,8 @@ def main():
             # BASELINE.json's metric asks for the fraction of the SLOWER of the INT32-issue and HBM rooflines.  This path is
             # INT32-issue bound (50-90x further from the HBM roof), so `roofline` is the INT32 view and the HBM view rides
             # inside it.  Both are timed in the bench configuration (filter 8 / KernelIdx 2, costs + decisions).  frac: the
-            # kernel alone, launches back to back on one stream (each launch pays its own ramp-up and tail);
+            # kernel alone, one frame at a time (launches back to back on one stream, each paying its own ramp-up and tail;
+            # the engine's lone-frame block split);
             # frac_timed_region: the same launches inside the timed region, where frames overlap on the slot streams
             # (timed-region time / launches = what one launch costs the GPU in steady state).
             "roofline": {"bound": "int32", "kernel": "mip_cost_kernel",

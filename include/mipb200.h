@@ -111,6 +111,17 @@ int mipb200_submit(mipb200_engine* e, const uint16_t* frame, int64_t poc);
 int mipb200_collect(mipb200_engine* e, mipb200_result* out);
 
 int mipb200_in_flight(const mipb200_engine* e);
+
+/* How the frame's work is cut into thread blocks.  A frame that has the GPU to itself wants its last blocks short (the
+ * frame's tail is then short: lowest latency of one frame); frames that overlap on the GPU -- several in flight, or
+ * device-resident launches on several streams -- fill each other's tails and want few, equal blocks (fewest tile
+ * stagings: highest frames/s).  AUTO (the default): mipb200_submit() uses the latency split when nothing else is in
+ * flight and the throughput split otherwise; mipb200_run_device() uses the throughput split.  Results are identical
+ * either way.  No reference counterpart (its NDRanges are fixed, main.cpp:1011-1200). */
+#define MIPB200_LAUNCH_AUTO 0
+#define MIPB200_LAUNCH_THROUGHPUT 1
+#define MIPB200_LAUNCH_LATENCY 2
+int mipb200_set_launch_mode(mipb200_engine* e, int mode);
 int mipb200_num_ctus(int width, int height);
 
 /* Number of CUDA devices (>= 0), or a negative MIPB200_E* code.  Replaces the reference's platform / device scan

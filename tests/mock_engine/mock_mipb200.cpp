@@ -53,6 +53,7 @@ MOCK_API int mipb200_unpin_host(void*) { return 0; }
 MOCK_API int mipb200_device_energy_mj(int, unsigned long long*) { strcpy(g_err, "mock: no energy counter"); return MIPB200_ENODEV; }
 MOCK_API long long mipb200_kernel_launches(const mipb200_engine*) { return 0; }
 MOCK_API int mipb200_in_flight(const mipb200_engine* e) { return (int)e->fifo.size(); }
+MOCK_API int mipb200_set_launch_mode(mipb200_engine*, int) { return 0; }
 
 MOCK_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) {
     if (cfg->width % 8 || cfg->height % 4 || cfg->device >= mipb200_device_count()) { strcpy(g_err, "mock: bad configuration"); return MIPB200_EINVAL; }

@@ -173,3 +173,31 @@ def test_repeated_launches_are_bit_identical(mip):
             c, m, b = outs[k]
             eng.run_device(fs[it % 2].data_ptr(), c.data_ptr(), d_best_mode=m.data_ptr(), d_best_cost=b.data_ptr(), stream=streams[k % 3].cuda_stream)
         torch.cuda.synchronize()
+
+
+def test_launch_modes_give_identical_results(mip, oracle):
+    """The throughput and the lone-frame split of a frame's work (mipb200_set_launch_mode) are two schedules of the same
+    arithmetic: tables and decisions are identical, for the host path (AUTO picks either, by what is in flight) and for the
+    device path."""
+    import torch
+    from mipb200 import frames
+    W, H = 384, 200
+    fs = [frames.noise_frame(W, H, 900 + i) for i in range(4)]
+    want = [oracle.run_frame(f, 7, 1) for f in fs]
+    for mode in (mip.LAUNCH_AUTO, mip.LAUNCH_THROUGHPUT, mip.LAUNCH_LATENCY):
+        with mip.Engine(W, H, filter_type=7, kernel_idx=1, slots=3, emit=mip.EMIT_COSTS | mip.EMIT_DECISIONS) as eng:
+            eng.set_launch_mode(mode)
+            for i, f in enumerate(fs[:3]):
+                eng.submit(f, i)               # AUTO: frame 0 enters an empty pipeline, 1 and 2 do not
+            for i in range(3):
+                r = eng.collect()
+                bm, bc = oracle.decisions(want[i])
+                assert np.array_equal(r.cost, want[i]) and np.array_equal(r.best_mode, bm) and np.array_equal(r.best_cost, bc), (mode, i)
+            d_f = torch.from_numpy(fs[3].view(np.int16)).cuda()
+            d_c = torch.empty((eng.n_ctus, mip.COSTS_PER_CTU), dtype=torch.int32, device="cuda")
+            eng.run_device(d_f.data_ptr(), d_c.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_c.cpu().numpy(), want[3]), mode
+    with pytest.raises(mip.MipError):
+        with mip.Engine(W, H, slots=1) as eng:
+            eng.set_launch_mode(7)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""One configuration of the chunk split (MIPB200_CHUNKS / MIPB200_CHUNK_WEIGHTS in the environment): ms per 1080p
+"""One configuration of the chunk split (MIPB200_CHUNK_WEIGHTS / MIPB200_CHUNK_WEIGHTS_LONE and MODE=auto|throughput|latency
+in the environment): ms per 1080p
 frame of the fused kernel (bench configuration: filter 8 / k 2, costs + decisions) with launches back to back on one
 stream (what a lone frame costs) and with frames round-robin over three streams (steady state).  Prints one JSON line."""
 import json
@@ -18,10 +19,13 @@ W, H = (int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "1920x1080").spli
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 96
 emit = mipb200.EMIT_COSTS | mipb200.EMIT_DECISIONS
 pool = torch.from_numpy(np.stack([frames.natural_frame(W, H, i) for i in range(4)]).view(np.int16)).cuda()
-res = {"chunks": os.environ.get("MIPB200_CHUNKS"), "weights": os.environ.get("MIPB200_CHUNK_WEIGHTS"), "size": f"{W}x{H}"}
+mode = {"auto": mipb200.LAUNCH_AUTO, "throughput": mipb200.LAUNCH_THROUGHPUT, "latency": mipb200.LAUNCH_LATENCY}[os.environ.get("MODE", "auto")]
+res = {"weights": os.environ.get("MIPB200_CHUNK_WEIGHTS"), "weights_lone": os.environ.get("MIPB200_CHUNK_WEIGHTS_LONE"), "mode": os.environ.get("MODE", "auto"), "size": f"{W}x{H}"}
 for ns in (1, 3):
     engs = [mipb200.Engine(W, H, filter_type=8, kernel_idx=2, slots=1, emit=emit) for _ in range(ns)]
     n = engs[0].n_ctus
+    for e_ in engs:
+        e_.set_launch_mode(mode)
     outs = [(torch.empty((n, mipb200.COSTS_PER_CTU), dtype=torch.int32, device="cuda"), torch.empty((n, mipb200.CUS_PER_CTU), dtype=torch.uint8, device="cuda"),
              torch.empty((n, mipb200.CUS_PER_CTU), dtype=torch.int32, device="cuda")) for _ in range(3)]
     streams = [torch.cuda.Stream() for _ in range(ns)]

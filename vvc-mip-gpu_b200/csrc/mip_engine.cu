@@ -111,9 +111,7 @@ struct mipb200_engine {
     // frames (measured: 850 frames/s with full tables at 1080p; in order: the link rate with the same 3 slots).
     cudaStream_t d2h_stream = nullptr;
     mipb200::FilterParams fp;         // fused low-pass filter of this configuration
-    // The kernel's CTAs are persistent and take their work from a few words in global memory that the kernel itself
-    // leaves zeroed: launches that share them must not overlap, so there is one set per stream the engine launches on.
-    std::vector<std::pair<cudaStream_t, int*>> sched;
+    int launch_mode = MIPB200_LAUNCH_AUTO;
     FILE* trace = nullptr;            // MIPB200_TRACE=<file>: per-frame device timeline (debugging aid, not API)
     cudaEvent_t ev_base = nullptr;
 };
@@ -166,10 +164,10 @@ static int check_cfg(const mipb200_config* c) {
 static void free_slot(Slot& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFreeHost(s.h_frame); cudaFreeHost(s.h_cost); cudaFreeHost(s.h_sad); cudaFreeHost(s.h_satd);
-    cudaFreeHost(s.h_best_cost); cudaFreeHost(s.h_best_mode); cudaFreeHost(s.h_topk_mode); cudaFreeHost(s.h_topk_cost);
-    cudaFree(s.d_topk_mode); cudaFree(s.d_topk_cost);
+    cudaFreeHost(s.h_best_cost); cudaFreeHost(s.h_topk_cost);      // the mode arrays live in the same allocations
+    cudaFree(s.d_topk_cost);
     cudaFree(s.d_frame); cudaFree(s.d_cost); cudaFree(s.d_sad); cudaFree(s.d_satd);
-    cudaFree(s.d_best_cost); cudaFree(s.d_best_mode);
+    cudaFree(s.d_best_cost);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
@@ -185,7 +183,6 @@ MIPB200_API void mipb200_destroy(mipb200_engine* e) {
     for (auto& s : e->slots) free_slot(s);
     if (e->d2h_stream) { cudaStreamSynchronize(e->d2h_stream); cudaStreamDestroy(e->d2h_stream); }
     if (e->aux_stream) { cudaStreamSynchronize(e->aux_stream); cudaStreamDestroy(e->aux_stream); }
-    for (auto& p : e->sched) cudaFree(p.second);
     if (e->ev_base) cudaEventDestroy(e->ev_base);
     if (e->trace) fclose(e->trace);
     delete e;
@@ -207,28 +204,35 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
     {
         std::lock_guard<std::mutex> lk(g_init_mutex);
         if (!g_dev_init[cfg->device]) {
-            // own units per CTU half: the 12-mode half of a half's work is cut into that many pieces (the other half, the
-            // tail, is shared task by task; see mip_cost_kernel).  Tuning knobs, not API: MIPB200_CHUNKS=n (equal shares),
-            // MIPB200_CHUNK_WEIGHTS=a,b,.. (relative cost shares).
-            int chunks = 2;
-            double weights[64];
-            bool haveW = false;
-            if (const char* ew = getenv("MIPB200_CHUNK_WEIGHTS")) {
-                chunks = 0;
-                for (const char* p = ew; *p && chunks < 64;) {
+            // Chunks per CTU half (= CTAs per half), two splits (see kernels_init): with frames overlapping on the slot
+            // streams 3 equal shares are the throughput optimum (0.435 ms per 1080p frame; 4 chunks: 0.449); a lone frame
+            // wants its last CTAs short: shares 4:3:2:1 (0.48 ms instead of 0.52).  Tuning knobs, not API:
+            // MIPB200_CHUNK_WEIGHTS=a,b,c,.. / MIPB200_CHUNK_WEIGHTS_LONE=a,b,c,.. (relative cost shares in launch order).
+            static const double kEqual3[3] = {1, 1, 1}, kLone[4] = {4, 3, 2, 1};
+            double wbuf[2][64];
+            int nchunks[2] = {3, 4};
+            const double* weights[2] = {kEqual3, kLone};
+            const char* names[2] = {"MIPB200_CHUNK_WEIGHTS", "MIPB200_CHUNK_WEIGHTS_LONE"};
+            for (int sp = 0; sp < 2; ++sp) {
+                const char* ew = getenv(names[sp]);
+                if (!ew) continue;
+                int n = 0;
+                for (const char* p = ew; *p && n < 64;) {
                     char* end = nullptr;
                     const double w = strtod(p, &end);
-                    if (end == p || !(w > 0)) return fail(MIPB200_EINVAL, "MIPB200_CHUNK_WEIGHTS=\"%s\": need positive numbers separated by commas", ew);
-                    weights[chunks++] = w;
+                    if (end == p || !(w > 0) || (*end && *end != ','))
+                        return fail(MIPB200_EINVAL, "%s=\"%s\": need positive numbers separated by commas", names[sp], ew);
+                    wbuf[sp][n++] = w;
                     p = *end == ',' ? end + 1 : end;
-                    if (*end && *end != ',') return fail(MIPB200_EINVAL, "MIPB200_CHUNK_WEIGHTS=\"%s\": need positive numbers separated by commas", ew);
                 }
-                haveW = chunks > 0;
-            } else if (const char* ev = getenv("MIPB200_CHUNKS")) {
-                chunks = atoi(ev);
+                if (n < 2) return fail(MIPB200_EINVAL, "%s=\"%s\": need at least two chunks (one chunk would hold more CUs than the kernel's decision table)", names[sp], ew);
+                nchunks[sp] = n;
+                weights[sp] = wbuf[sp];
             }
-            if (chunks < 1 || chunks > 64) return fail(MIPB200_EINVAL, "%d own units per CTU half: need 1..64", chunks);
-            CU_TRY(mipb200::kernels_init(chunks, haveW ? weights : nullptr));
+            const cudaError_t ke = mipb200::kernels_init(nchunks, weights);
+            if (ke == cudaErrorInvalidValue)
+                return fail(MIPB200_EINVAL, "a chunk split puts more than 2048 CUs into one chunk; use more chunks or more even weights");
+            CU_TRY(ke);
             g_dev_init[cfg->device] = true;
         }
     }
@@ -270,10 +274,10 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
             if (wc) E_TRY(cudaHostAlloc((void**)&s.h_cost, e->cost_bytes, cudaHostAllocDefault));
         }
         if (tk) {
-            E_TRY(cudaMalloc((void**)&s.d_topk_mode, e->cu_bytes1 * tk));
-            E_TRY(cudaMalloc((void**)&s.d_topk_cost, e->cu_bytes4 * tk));
-            E_TRY(cudaHostAlloc((void**)&s.h_topk_mode, e->cu_bytes1 * tk, cudaHostAllocDefault));
-            E_TRY(cudaHostAlloc((void**)&s.h_topk_cost, e->cu_bytes4 * tk, cudaHostAllocDefault));
+            E_TRY(cudaMalloc((void**)&s.d_topk_cost, (e->cu_bytes4 + e->cu_bytes1) * tk));
+            E_TRY(cudaHostAlloc((void**)&s.h_topk_cost, (e->cu_bytes4 + e->cu_bytes1) * tk, cudaHostAllocDefault));
+            s.d_topk_mode = reinterpret_cast<uint8_t*>(s.d_topk_cost) + e->cu_bytes4 * tk;
+            s.h_topk_mode = reinterpret_cast<uint8_t*>(s.h_topk_cost) + e->cu_bytes4 * tk;
         }
         if (ws) {
             E_TRY(cudaMalloc((void**)&s.d_sad, e->cost_bytes));
@@ -281,11 +285,11 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
             E_TRY(cudaHostAlloc((void**)&s.h_sad, e->cost_bytes, cudaHostAllocDefault));
             E_TRY(cudaHostAlloc((void**)&s.h_satd, e->cost_bytes, cudaHostAllocDefault));
         }
-        if (wd) {
-            E_TRY(cudaMalloc((void**)&s.d_best_mode, e->cu_bytes1));
-            E_TRY(cudaMalloc((void**)&s.d_best_cost, e->cu_bytes4));
-            E_TRY(cudaHostAlloc((void**)&s.h_best_mode, e->cu_bytes1, cudaHostAllocDefault));
-            E_TRY(cudaHostAlloc((void**)&s.h_best_cost, e->cu_bytes4, cudaHostAllocDefault));
+        if (wd) {   // best costs and best modes share one buffer (int32 part first): one read-back copy per frame
+            E_TRY(cudaMalloc((void**)&s.d_best_cost, e->cu_bytes4 + e->cu_bytes1));
+            E_TRY(cudaHostAlloc((void**)&s.h_best_cost, e->cu_bytes4 + e->cu_bytes1, cudaHostAllocDefault));
+            s.d_best_mode = reinterpret_cast<uint8_t*>(s.d_best_cost) + e->cu_bytes4;
+            s.h_best_mode = reinterpret_cast<uint8_t*>(s.h_best_cost) + e->cu_bytes4;
         }
     }
 #undef E_TRY
@@ -305,6 +309,13 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
 }
 
 MIPB200_API int mipb200_in_flight(const mipb200_engine* e) { return e ? e->in_flight : 0; }
+
+MIPB200_API int mipb200_set_launch_mode(mipb200_engine* e, int mode) {
+    if (!e) return fail(MIPB200_EINVAL, "engine is NULL");
+    if (mode != MIPB200_LAUNCH_AUTO && mode != MIPB200_LAUNCH_THROUGHPUT && mode != MIPB200_LAUNCH_LATENCY) return fail(MIPB200_EINVAL, "launch mode %d unknown", mode);
+    e->launch_mode = mode;
+    return MIPB200_OK;
+}
 MIPB200_API long long mipb200_kernel_launches(const mipb200_engine* e) { return e ? e->launches : 0; }
 
 // pinned staging frame of a slot: only callers that hand over pageable memory or fill mipb200_next_input() need one
@@ -324,16 +335,9 @@ MIPB200_API uint16_t* mipb200_next_input(mipb200_engine* e) {
 
 // one fused kernel per frame: (filter +) boundaries + prediction + costs + per-CU argmin; counts launches
 static int enqueue_kernels(mipb200_engine* e, const uint16_t* d_frame, int32_t* d_cost, int32_t* d_sad,
-                           int32_t* d_satd, uint8_t* d_bm, int32_t* d_bc, cudaStream_t st) {
+                           int32_t* d_satd, uint8_t* d_bm, int32_t* d_bc, bool lone, cudaStream_t st) {
     const mipb200_config& c = e->cfg;
-    int* sch = nullptr;
-    for (auto& p : e->sched)
-        if (p.first == st) { sch = p.second; break; }
-    if (!sch) {
-        CU_TRY(mipb200::sched_alloc(c.width, c.height, &sch));
-        e->sched.emplace_back(st, sch);
-    }
-    CU_TRY(mipb200::launch_costs(d_frame, c.width, c.height, c.bit_depth, e->fp, d_cost, d_sad, d_satd, d_bm, d_bc, sch, st));
+    CU_TRY(mipb200::launch_costs(d_frame, c.width, c.height, c.bit_depth, e->fp, d_cost, d_sad, d_satd, d_bm, d_bc, lone, st));
     e->launches++;
     return MIPB200_OK;
 }
@@ -362,10 +366,12 @@ MIPB200_API int mipb200_submit(mipb200_engine* e, const uint16_t* frame, int64_t
         }
     }
     s.poc = poc;
-    CU_TRY(cudaEventRecord(s.ev_start, s.stream));
+    if (e->trace) CU_TRY(cudaEventRecord(s.ev_start, s.stream));       // every runtime call in here is paid per frame, on every GPU's thread
     CU_TRY(cudaMemcpyAsync(s.d_frame, src, e->frame_bytes, cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaEventRecord(s.ev_k0, s.stream));
-    int rc = enqueue_kernels(e, s.d_frame, s.d_cost, s.d_sad, s.d_satd, s.d_best_mode, s.d_best_cost, s.stream);
+    // a frame submitted into an empty pipeline has the GPU to itself (at least at its start): the lone-frame split
+    const bool lone = e->launch_mode == MIPB200_LAUNCH_LATENCY || (e->launch_mode == MIPB200_LAUNCH_AUTO && e->in_flight == 0);
+    int rc = enqueue_kernels(e, s.d_frame, s.d_cost, s.d_sad, s.d_satd, s.d_best_mode, s.d_best_cost, lone, s.stream);
     if (rc) return rc;
     if (s.d_topk_mode) {
         CU_TRY(mipb200::launch_topk(s.d_cost, e->n_ctus, e->cfg.top_k, s.d_topk_mode, s.d_topk_cost, s.stream));
@@ -374,14 +380,8 @@ MIPB200_API int mipb200_submit(mipb200_engine* e, const uint16_t* frame, int64_t
     CU_TRY(cudaEventRecord(s.ev_k1, s.stream));
     cudaStream_t rb = e->d2h_stream;           // in-order read-back: decisions first (small), then the tables
     CU_TRY(cudaStreamWaitEvent(rb, s.ev_k1, 0));
-    if (s.h_best_mode) {
-        CU_TRY(cudaMemcpyAsync(s.h_best_mode, s.d_best_mode, e->cu_bytes1, cudaMemcpyDeviceToHost, rb));
-        CU_TRY(cudaMemcpyAsync(s.h_best_cost, s.d_best_cost, e->cu_bytes4, cudaMemcpyDeviceToHost, rb));
-    }
-    if (s.h_topk_mode) {
-        CU_TRY(cudaMemcpyAsync(s.h_topk_mode, s.d_topk_mode, e->cu_bytes1 * e->cfg.top_k, cudaMemcpyDeviceToHost, rb));
-        CU_TRY(cudaMemcpyAsync(s.h_topk_cost, s.d_topk_cost, e->cu_bytes4 * e->cfg.top_k, cudaMemcpyDeviceToHost, rb));
-    }
+    if (s.h_best_cost) CU_TRY(cudaMemcpyAsync(s.h_best_cost, s.d_best_cost, e->cu_bytes4 + e->cu_bytes1, cudaMemcpyDeviceToHost, rb));
+    if (s.h_topk_cost) CU_TRY(cudaMemcpyAsync(s.h_topk_cost, s.d_topk_cost, (e->cu_bytes4 + e->cu_bytes1) * e->cfg.top_k, cudaMemcpyDeviceToHost, rb));
     if (s.h_cost) CU_TRY(cudaMemcpyAsync(s.h_cost, s.d_cost, e->cost_bytes, cudaMemcpyDeviceToHost, rb));
     if (s.h_sad) {
         CU_TRY(cudaMemcpyAsync(s.h_sad, s.d_sad, e->cost_bytes, cudaMemcpyDeviceToHost, rb));
@@ -436,7 +436,8 @@ MIPB200_API int mipb200_run_device(mipb200_engine* e, const uint16_t* d_frame, i
     DeviceGuard dg(e->cfg.device);
     CU_TRY(dg.err);
     cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
-    return enqueue_kernels(e, d_frame, d_cost, d_sad, d_satd, d_best_mode, d_best_cost, st);
+    // the caller's streams are its business: unless told otherwise (mipb200_set_launch_mode) launches are assumed to overlap
+    return enqueue_kernels(e, d_frame, d_cost, d_sad, d_satd, d_best_mode, d_best_cost, e->launch_mode == MIPB200_LAUNCH_LATENCY, st);
 }
 
 MIPB200_API int mipb200_filter_device(mipb200_engine* e, const uint16_t* d_frame, uint16_t* d_out, void* stream) {

@@ -82,8 +82,8 @@ constexpr int SM_REF = SM_ORIG + SM_ORIG_BYTES;
 constexpr int SM_REF_BYTES = (RT_SLOTS * RT_STRIDE + RL_SLOTS * RL_STRIDE) * 2;   // 9792
 constexpr int SM_MAT = SM_REF + SM_REF_BYTES;
 constexpr int SM_MISC = SM_MAT + ((MAT_BYTES + 15) / 16) * 16; // s_dc, work counter, mbarrier
-constexpr int SM_DEC = SM_MISC + 64;                            // u32[DEC_MAX]: min over modes of (cost << 6 | mode) of an own unit's CUs
-constexpr int SM_TOTAL = SM_DEC + 640 * 4;
+constexpr int SM_DEC = SM_MISC + 32;                            // u32[DEC_MAX]: min over modes of (cost << 6 | mode)
+constexpr int SM_TOTAL = SM_DEC + 2048 * 4;
 
 // TMA staging box: frame rows tileY-3 .. tileY+65, columns ctuX-8 .. ctuX+135 (halo 3 >= filter radius 2 + the
 // boundary halo 1; 8 columns on the left keep every row 16-byte aligned).  It overlays the s_red scratch.
@@ -102,22 +102,19 @@ struct DevType {               // what device code needs to know about a CU type
 };
 
 __constant__ DevType c_types[MIP_NUM_TYPES];
-// Work of a CTU half = a list of warp tasks in descending cost order: first the tasks of the 12-mode CU types (sizeId 2),
-// then those of the 16- and 32-mode types (sizeId 1 and 0).  A CU of a 12-mode type can straddle two warp tasks, so its
-// decision is merged in shared memory and that part of the list is cut into `chunks` contiguous, cost-balanced OWN units
-// (never splitting a CU) that one CTA works through alone.  A CU of the other types sits inside one warp task, its decision
-// is stored by the warp that computed it, and that part of the list -- the TAIL, about half of the work, short tasks --
-// can be shared by any number of CTAs, task by task.
-__constant__ int c_chunk_begin[2][MAX_CHUNKS + 1];      // first task of each own unit (per half); [chunks] = first tail task
-__constant__ int c_tasks[2];                            // tasks per half (own + tail)
-// fused decisions of the own units
-constexpr int DEC_MAX = 640;                   // 12-mode CUs per CTU half: 578
-__constant__ uint16_t c_chunk_ord[2][MAX_CHUNKS + 1];   // first 12-mode CU (ordinal inside the half) of each own unit
-__constant__ uint16_t c_ord2cu[2][DEC_MAX];    // ordinal of a 12-mode CU inside a half -> CU index inside the CTU (0..5379)
+// Two splits of a half's work list into chunks are kept side by side: [0] for throughput (frames overlap on the GPU, tails
+// are filled by the next frame: few, equal chunks = fewest tile stagings) and [1] for a lone frame (decreasing shares: the
+// CTAs that run last are short, so the frame's tail is).  A launch names the one it wants.
+__constant__ int c_chunks[2];
+__constant__ int c_chunk_begin[2][2][MAX_CHUNKS + 1];
+// fused decisions: a chunk never splits the modes of a CU, so the CTA owns the argmin of its CUs
+constexpr int DEC_MAX = 2048;                  // CUs per chunk the shared-memory argmin table can hold
+__constant__ uint16_t c_chunk_ord[2][2][MAX_CHUNKS + 1];   // first CU ordinal of each chunk (per split and half)
+__constant__ uint16_t c_ord2cu[2][2700];       // CU ordinal inside a half -> CU index inside the CTU (0..5379)
 __device__ uint2 g_lane[2][MAX_WORK][32];      // per (half, warp task, lane): what the lane does, see the task loop of mip_cost_kernel
 __device__ uint8_t g_mat[MAT_BYTES];           // (coef - 32) as signed bytes, padded layout above
 
-static int g_chunks = 0;
+static int g_chunks[2] = {0, 0};
 
 // the 17 distinct CU shapes
 enum Shape {
@@ -618,24 +615,10 @@ __device__ __forceinline__ void build_ref_tile(uint16_t* s_refT, uint16_t* s_ref
 // ------------------------------------------------------------------------------------------
 // The fused kernel
 // ------------------------------------------------------------------------------------------
-// Scheduler words of one launch, in global memory (zero when the kernel starts; the last CTA to leave zeroes them again):
-constexpr int SCH_OWN = 0;      // next own unit (chunk-major: unit u = chunk u / halves of half u % halves)
-constexpr int SCH_TAIL = 1;     // next tail that nobody has started yet
-constexpr int SCH_DONE = 2;     // CTAs that have left
-constexpr int SCH_HALF0 = 3;    // + h: next tail task of half h
-constexpr int MIN_STEAL = 64;   // tail tasks that must be left for another CTA to join (it stages the tile first: ~12 tasks' worth)
-
-// PERSISTENT CTAs, two work queues.  Every CTA first takes own units (a CTU half's tile is staged, the unit's tasks are
-// drawn by the CTA's warps from a shared-memory counter, 12-mode decisions are merged in shared memory and written at the
-// end of the unit) until none is left; then tails: it claims a tail nobody has started, stages the half and draws its
-// tasks from the half's GLOBAL counter; when every tail has been started it joins the tail with the most tasks left, and
-// leaves when no tail has MIN_STEAL tasks left.  No CTA ever waits for another one, so the grid need not be co-resident.
-// A lone frame no longer pays for wave quantisation (810 CTAs over 296 slots = 2.74 waves) or a ragged tail: all CTAs run
-// out of work together.
 __global__ void __launch_bounds__(NT, 2)
-mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams fp, int W, int H, int chunks, int maxv,
+mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams fp, int W, int H, int split, int maxv,
                 int32_t* __restrict__ g_cost, int32_t* __restrict__ g_sad, int32_t* __restrict__ g_satd,
-                uint8_t* __restrict__ g_best_mode, int32_t* __restrict__ g_best_cost, int* __restrict__ sched) {
+                uint8_t* __restrict__ g_best_mode, int32_t* __restrict__ g_best_cost) {
     extern __shared__ __align__(128) unsigned char smem[];
     int* s_orig = reinterpret_cast<int*>(smem + SM_ORIG);
     uint16_t* s_refT = reinterpret_cast<uint16_t*>(smem + SM_REF);
@@ -644,21 +627,61 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     uint16_t* s_stg = reinterpret_cast<uint16_t*>(smem + SM_RED);    // TMA box, dead before the first task starts
     uint8_t* s_mat = smem + SM_MAT;
     uint16_t* s_dc = reinterpret_cast<uint16_t*>(smem + SM_MISC);
-    int* s_next = reinterpret_cast<int*>(smem + SM_MISC + 4);        // task counter of an own unit
-    int* s_asg = reinterpret_cast<int*>(smem + SM_MISC + 8);         // assignment: [0] half (-1: leave), [1] own chunk (-1: tail)
+    int* s_next = reinterpret_cast<int*>(smem + SM_MISC + 4);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + SM_MISC + 16);
     uint32_t* s_dec = reinterpret_cast<uint32_t*>(smem + SM_DEC);
 
     const int tid = threadIdx.x, lane = tid & 31;
+    // chunk-major unit order: CTAs that are resident together work on the same chunk (the same CU
+    // shapes, hence the same code) of different CTU halves, which keeps the instruction caches warm
     const int ctuCols = (W + 127) >> 7;
     const int halves = 2 * ctuCols * ((H + 127) >> 7);
-    const int ownUnits = chunks * halves;
+    const int chunk = blockIdx.x / halves, hu = blockIdx.x - chunk * halves;
+    const int ctu = hu >> 1, half = hu & 1;
+    const int ctuX = (ctu % ctuCols) << 7, tileY = ((ctu / ctuCols) << 7) + half * TILE_ROWS;
+    const int rowsValid = min(TILE_ROWS, H - tileY);     // <= 0: the whole half lies below the frame
+    const int wbeg = c_chunk_begin[split][half][chunk], wcnt = c_chunk_begin[split][half][chunk + 1] - wbeg;
+    const uint32_t ctuBase = (uint32_t)ctu * MIP_COSTS_PER_CTU;   // 32-bit element index: frames up to 43 000 CTUs
 
-    // ---- once per CTA: matrices, the barrier of the TMA box, the default sample
-    for (int i = tid; i < MAT_BYTES / 4; i += NT)
-        reinterpret_cast<uint32_t*>(s_mat)[i] = reinterpret_cast<const uint32_t*>(g_mat)[i];
-    if (tid == 0) { mbar_init(s_bar, 1); *s_dc = (uint16_t)((maxv + 1) >> 1); }
-    uint32_t boxes = 0;       // TMA boxes this CTA has waited for: the barrier's phase parity
+    if (rowsValid > 0) {
+        // ---- stage: one TMA box (tile + halo) signalled on an mbarrier; the matrices come in meanwhile
+        if (tid == 0) {
+            mbar_init(s_bar, 1);
+            mbar_expect_tx(s_bar, STG_BYTES);
+            tma_load_2d(s_stg, &tmap, ctuX - STG_X0, tileY - STG_Y0, s_bar);
+        }
+        for (int i = tid; i < MAT_BYTES / 4; i += NT)
+            reinterpret_cast<uint32_t*>(s_mat)[i] = reinterpret_cast<const uint32_t*>(g_mat)[i];
+        __syncthreads();                                  // the barrier word is initialised for everyone
+        if (!mbar_try_wait(s_bar, 0)) {
+            // a lost TMA must not hang the GPU: give up after 4 s of wall time (time-based, so that a sanitizer or a
+            // debugger slowing the kernel down by orders of magnitude cannot trip it)
+            const uint64_t t0 = globaltimer_ns();
+            while (!mbar_try_wait(s_bar, 0))
+                if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+        }
+        // ---- originals (+1) as int32 (see diff_shifted()); rows below the frame are TMA zero fill
+        for (int i = tid; i < TILE_ROWS * 16; i += NT) {
+            const int y = i >> 4, xc = (i & 15) << 3;
+            const uint4 v = *reinterpret_cast<const uint4*>(s_stg + (y + STG_Y0) * STG_W + STG_X0 + xc);
+            int4* dst = reinterpret_cast<int4*>(s_orig + y * OS + xc);
+            dst[0] = make_int4((v.x & 0xffff) + 1, (v.x >> 16) + 1, (v.y & 0xffff) + 1, (v.y >> 16) + 1);
+            dst[1] = make_int4((v.z & 0xffff) + 1, (v.z >> 16) + 1, (v.w & 0xffff) + 1, (v.w >> 16) + 1);
+        }
+        // ---- reference row/column slots: copy, or the fused low-pass filter (fp.type = 1..8)
+        switch (fp.type) {
+            case 0:         build_ref_tile<1, true, false>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            case 1: case 2: build_ref_tile<1, false, true>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            case 3: case 4: build_ref_tile<1, true, true>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            case 5: case 6: build_ref_tile<2, false, true>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            default:        build_ref_tile<2, true, true>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
+        }
+    }
+    const int ordBeg = c_chunk_ord[split][half][chunk], ordCnt = c_chunk_ord[split][half][chunk + 1] - ordBeg;
+    if (g_best_mode)
+        for (int i = tid; i < ordCnt; i += NT) s_dec[i] = 0xffffffffu;
+    if (tid == 0) { *s_dc = (uint16_t)((maxv + 1) >> 1); *s_next = 0; }
+    __syncthreads();                                      // tiles complete; the staging box may now be overwritten
 
     Ctx c;
     c.s_orig = s_orig;
@@ -669,199 +692,104 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     c.maxv2 = (uint32_t)maxv * 0x10001u;
     c.s_red = s_red + tid;
     c.s_mat = s_mat;
+    c.ctuX = ctuX;
+    c.tileY = tileY;
 
-    for (;;) {
-        __syncthreads();      // the previous assignment is finished: tiles, cells and s_asg may be overwritten
-        // ---- what next?  (warp 0 decides)
-        if (tid < 32) {
-            int h = -1, chunk = -1;
-            int u = ownUnits;
-            if (lane == 0 && *reinterpret_cast<volatile int*>(sched + SCH_OWN) < ownUnits) u = atomicAdd(sched + SCH_OWN, 1);
-            u = __shfl_sync(0xffffffffu, u, 0);
-            if (u < ownUnits) {
-                // chunk-major order: CTAs that are resident together work on the same chunk (the same CU shapes, hence the
-                // same code) of different CTU halves, which keeps the instruction caches warm
-                chunk = u / halves;
-                h = u - chunk * halves;
-            } else {
-                int t = halves;
-                if (lane == 0 && *reinterpret_cast<volatile int*>(sched + SCH_TAIL) < halves) t = atomicAdd(sched + SCH_TAIL, 1);
-                t = __shfl_sync(0xffffffffu, t, 0);
-                if (t < halves) h = t;
-                else {
-                    // every tail has been started: join the one with the most tasks left (ties broken differently by every CTA)
-                    uint32_t best = 0;
-                    int bh = -1;
-                    for (int i = lane; i < halves; i += 32) {
-                        const int left = c_tasks[i & 1] - c_chunk_begin[i & 1][chunks] - *reinterpret_cast<volatile int*>(sched + SCH_HALF0 + i);
-                        const uint32_t key = left >= MIN_STEAL ? ((uint32_t)left << 8) | ((uint32_t)(i * 40503u + blockIdx.x * 2654435761u) >> 24) : 0u;
-                        if (key > best) { best = key; bh = i; }
-                    }
-                    const uint32_t top = __reduce_max_sync(0xffffffffu, best);
-                    if (top) {
-                        const unsigned who = __ballot_sync(0xffffffffu, best == top);
-                        h = __shfl_sync(0xffffffffu, bh, __ffs(who) - 1);
-                    }
-                }
+    // Warp tasks are drawn from a shared-memory counter, one ahead: the record of the next task (one coalesced 8-byte load
+    // from a table built once on the host -- the same 870 KB for every CTU, so it lives in L2) is requested before the
+    // current task's arithmetic starts, which hides the atomic + L2 latency of the draw behind ~1000 instructions of work.
+    // Record: .x = cuX | cuY << 7 | mode << 13 | strip group << 18 | inRange << 20 | CU type << 21, .y = cost index in
+    // the CTU | decision slot << 17.  0xffffffff in .x = no more work.
+    auto draw = [&](uint32_t zero) -> uint2 {
+        // Lane 0 draws.  ptxas wraps an atomic on a warp-uniform address into a vote / popc / shuffle aggregation (17
+        // instructions); `zero` -- bits of a loaded record that are always 0, which the compiler cannot know -- makes the
+        // address formally per-lane and leaves a single predicated ATOMS.ADD.
+        int wi;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\tmov.s32 %0, 0;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
+                     : "=r"(wi) : "r"(lane), "r"(smem_u32(s_next) + zero) : "memory");
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (wi >= wcnt) return make_uint2(0xffffffffu, 0u);
+        return __ldg(&g_lane[half][wbeg + wi][lane]);
+    };
+    uint2 lr = draw((__ldg(&g_lane[half][min(wbeg, MAX_WORK - 1)][lane]).y >> 30) << 2);
+    while (lr.x != 0xffffffffu) {
+        const uint2 lr_next = draw((lr.y >> 30) << 2);
+        // warp task = 32 consecutive (CU, mode) pairs of one type: a warp touches at most 3-4 CUs, so the shared-memory
+        // reads of originals and boundaries are mostly broadcasts (8 CUs x 4 modes per warp measured 60 % more bank conflicts)
+        const DevType& ty = c_types[(lr.x >> 21) & 63];
+        const int pl2 = ty.parts_log2;
+        const int cuX = lr.x & 127, cuY = (lr.x >> 7) & 63, mode = (lr.x >> 13) & 31, part = (lr.x >> 18) & 3;
+        const bool inRange = (lr.x >> 20) & 1;
+        const uint32_t coff = lr.y & 0x1ffffu;
+        const int slot = (int)(lr.y >> 17);
+        const bool active = inRange && cuY + ty.h <= rowsValid && ctuX + cuX + ty.w <= W;   // CU fully inside the frame
+        int sad = 0, satd = 0;
+        if (__any_sync(0xffffffffu, active)) {
+            switch (ty.shape) {
+                case S64x64: run_task<2, 64, 64, 4>(c, cuX, cuY, mode, part, sad, satd); break;
+                case S32x32: run_task<2, 32, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S32x16: run_task<2, 32, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S16x32: run_task<2, 16, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S32x8:  run_task<2, 32, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S8x32:  run_task<2, 8, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S16x16: run_task<2, 16, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S16x8:  run_task<2, 16, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S8x16:  run_task<2, 8, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S32x4:  run_task<1, 32, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S4x32:  run_task<1, 4, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S16x4:  run_task<1, 16, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S4x16:  run_task<1, 4, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S8x8:   run_task<1, 8, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S8x4:   run_task<1, 8, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
+                case S4x8:   run_task<1, 4, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
+                default:     run_task<0, 4, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
             }
-            if (lane == 0) { s_asg[0] = h; s_asg[1] = chunk; *s_next = 0; }
-        }
-        __syncthreads();
-        const int hu = s_asg[0], chunk = s_asg[1];
-        if (hu < 0) break;
-        const bool own = chunk >= 0;
-        const int ctu = hu >> 1, half = hu & 1;
-        const int ctuX = (ctu % ctuCols) << 7, tileY = ((ctu / ctuCols) << 7) + half * TILE_ROWS;
-        const int rowsValid = min(TILE_ROWS, H - tileY);     // <= 0: the whole half lies below the frame
-        const int wbeg = c_chunk_begin[half][own ? chunk : chunks];
-        const int wcnt = (own ? c_chunk_begin[half][chunk + 1] : c_tasks[half]) - wbeg;
-        int* const ctr = own ? s_next : sched + SCH_HALF0 + hu;       // generic pointer: shared or global counter
-        const uint32_t ctuBase = (uint32_t)ctu * MIP_COSTS_PER_CTU;   // 32-bit element index: frames up to 43 000 CTUs
-        const size_t cuBase = (size_t)ctu * MIP_CUS_PER_CTU;
-        c.ctuX = ctuX;
-        c.tileY = tileY;
-
-        if (rowsValid > 0) {
-            // ---- stage: one TMA box (tile + halo) signalled on an mbarrier
-            if (tid == 0) {
-                mbar_expect_tx(s_bar, STG_BYTES);
-                tma_load_2d(s_stg, &tmap, ctuX - STG_X0, tileY - STG_Y0, s_bar);
-            }
-            if (!mbar_try_wait(s_bar, boxes & 1)) {
-                // a lost TMA must not hang the GPU: give up after 4 s of wall time (time-based, so that a sanitizer or a
-                // debugger slowing the kernel down by orders of magnitude cannot trip it)
-                const uint64_t t0 = globaltimer_ns();
-                while (!mbar_try_wait(s_bar, boxes & 1))
-                    if (globaltimer_ns() - t0 > 4000000000ull) __trap();
-            }
-            ++boxes;
-            // ---- originals (+1) as int32 (see diff_shifted()); rows below the frame are TMA zero fill
-            for (int i = tid; i < TILE_ROWS * 16; i += NT) {
-                const int y = i >> 4, xc = (i & 15) << 3;
-                const uint4 v = *reinterpret_cast<const uint4*>(s_stg + (y + STG_Y0) * STG_W + STG_X0 + xc);
-                int4* dst = reinterpret_cast<int4*>(s_orig + y * OS + xc);
-                dst[0] = make_int4((v.x & 0xffff) + 1, (v.x >> 16) + 1, (v.y & 0xffff) + 1, (v.y >> 16) + 1);
-                dst[1] = make_int4((v.z & 0xffff) + 1, (v.z >> 16) + 1, (v.w & 0xffff) + 1, (v.w >> 16) + 1);
-            }
-            // ---- reference row/column slots: copy, or the fused low-pass filter (fp.type = 1..8)
-            switch (fp.type) {
-                case 0:         build_ref_tile<1, true, false>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
-                case 1: case 2: build_ref_tile<1, false, true>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
-                case 3: case 4: build_ref_tile<1, true, true>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
-                case 5: case 6: build_ref_tile<2, false, true>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
-                default:        build_ref_tile<2, true, true>(s_refT, s_refL, s_stg, ctuX, tileY, W, H, fp, tid); break;
+            if (pl2) {   // lanes 4k..4k+3 hold the four strip groups of one (CU, mode)
+                sad += __shfl_xor_sync(0xffffffffu, sad, 1);  satd += __shfl_xor_sync(0xffffffffu, satd, 1);
+                sad += __shfl_xor_sync(0xffffffffu, sad, 2);  satd += __shfl_xor_sync(0xffffffffu, satd, 2);
             }
         }
-        const int ordBeg = own ? c_chunk_ord[half][chunk] : 0, ordCnt = own ? c_chunk_ord[half][chunk + 1] - ordBeg : 0;
-        if (g_best_mode)
-            for (int i = tid; i < ordCnt; i += NT) s_dec[i] = 0xffffffffu;
-        __syncthreads();                                      // tiles complete; the staging box may now be overwritten
-
-        // Warp tasks are drawn one ahead: the record of the next task (one coalesced 8-byte load from a table built once on
-        // the host -- the same 870 KB for every CTU, so it lives in L2) is requested before the current task's arithmetic
-        // starts, which hides the atomic + L2 latency of the draw behind ~1000 instructions of work.
-        // Record: .x = cuX | cuY << 7 | mode << 13 | strip group << 18 | inRange << 20 | CU type << 21, .y = cost index in
-        // the CTU | decision index << 17 (12-mode types: ordinal of the CU among the half's 12-mode CUs = its cell; other
-        // types: index of the CU inside the CTU).  0xffffffff in .x = no more work.
-        auto draw = [&](uint32_t zero) -> uint2 {
-            // Lane 0 draws.  ptxas wraps an atomic on a warp-uniform address into a vote / popc / shuffle aggregation (17
-            // instructions); `zero` -- bits of a loaded record that are always 0, which the compiler cannot know -- makes the
-            // address formally per-lane and leaves a single predicated atomic.
-            int wi;
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\tmov.s32 %0, 0;\n\t@p atom.add.u32 %0, [%2], 1;\n\t}"
-                         : "=r"(wi) : "r"(lane), "l"(reinterpret_cast<uint64_t>(ctr) + zero) : "memory");
-            wi = __shfl_sync(0xffffffffu, wi, 0);
-            if (wi >= wcnt) return make_uint2(0xffffffffu, 0u);
-            return __ldg(&g_lane[half][wbeg + wi][lane]);
-        };
-        uint2 lr = draw((__ldg(&g_lane[half][min(wbeg, MAX_WORK - 1)][lane]).y >> 30) << 2);
-        while (lr.x != 0xffffffffu) {
-            const uint2 lr_next = draw((lr.y >> 30) << 2);
-            // warp task = 32 consecutive (CU, mode) pairs of one type: a warp touches at most 3-4 CUs, so the shared-memory
-            // reads of originals and boundaries are mostly broadcasts (8 CUs x 4 modes per warp measured 60 % more bank conflicts)
-            const DevType& ty = c_types[(lr.x >> 21) & 63];
-            const int pl2 = ty.parts_log2;
-            const int cuX = lr.x & 127, cuY = (lr.x >> 7) & 63, mode = (lr.x >> 13) & 31, part = (lr.x >> 18) & 3;
-            const bool inRange = (lr.x >> 20) & 1;
-            const uint32_t coff = lr.y & 0x1ffffu;
-            const uint32_t di = lr.y >> 17;
-            const bool active = inRange && cuY + ty.h <= rowsValid && ctuX + cuX + ty.w <= W;   // CU fully inside the frame
-            int sad = 0, satd = 0;
-            if (__any_sync(0xffffffffu, active)) {
-                switch (ty.shape) {
-                    case S64x64: run_task<2, 64, 64, 4>(c, cuX, cuY, mode, part, sad, satd); break;
-                    case S32x32: run_task<2, 32, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S32x16: run_task<2, 32, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S16x32: run_task<2, 16, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S32x8:  run_task<2, 32, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S8x32:  run_task<2, 8, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S16x16: run_task<2, 16, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S16x8:  run_task<2, 16, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S8x16:  run_task<2, 8, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S32x4:  run_task<1, 32, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S4x32:  run_task<1, 4, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S16x4:  run_task<1, 16, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S4x16:  run_task<1, 4, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S8x8:   run_task<1, 8, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S8x4:   run_task<1, 8, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    case S4x8:   run_task<1, 4, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
-                    default:     run_task<0, 4, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
-                }
-                if (pl2) {   // lanes 4k..4k+3 hold the four strip groups of one (CU, mode)
-                    sad += __shfl_xor_sync(0xffffffffu, sad, 1);  satd += __shfl_xor_sync(0xffffffffu, satd, 1);
-                    sad += __shfl_xor_sync(0xffffffffu, sad, 2);  satd += __shfl_xor_sync(0xffffffffu, satd, 2);
-                }
-            }
+        if (inRange && part == 0) {
+            const uint32_t o = ctuBase + coff;
             const int cost = min(2 * sad, satd);            // intra.cl:1166
-            if (inRange && part == 0) {
-                const uint32_t o = ctuBase + coff;
-                if (g_cost) g_cost[o] = active ? cost : -1;
-                if (g_sad) { g_sad[o] = active ? sad : -1; g_satd[o] = active ? satd : -1; }   // both or neither (launch_costs)
-            }
-            if (g_best_mode) {
-                // decision = argmin over the CU's modes, lowest mode wins ties: min of (cost << 6 | mode), cost < 2^26
-                const int modes = ty.modes;
-                if (modes >= 16) {
-                    // 16 or 32 modes: a CU is exactly one half or one whole warp task (in range and active as a whole): its lanes
-                    // are reduced in registers (REDUX.MIN) and the group's first lane stores the decision
-                    const unsigned grp = modes == 32 ? 0xffffffffu : ((lane & 16) ? 0xffff0000u : 0x0000ffffu);
-                    const uint32_t best = __reduce_min_sync(grp, active ? ((uint32_t)cost << 6) | (uint32_t)mode : 0xffffffffu);
-                    if (inRange && (lane & (modes - 1)) == 0) {
-                        g_best_mode[cuBase + di] = best == 0xffffffffu ? (uint8_t)0xFF : (uint8_t)(best & 63u);
-                        g_best_cost[cuBase + di] = best == 0xffffffffu ? -1 : (int32_t)(best >> 6);
-                    }
-                } else {
-                    // 12 modes (and the 64x64 type's 48 lanes per CU): a CU can straddle two warp tasks, which two warps of the
-                    // CTA may hold: the lanes of a CU inside this task are reduced in registers (MATCH.ANY + REDUX.MIN), one
-                    // lane folds the result into the CU's shared-memory cell, and the CTA writes the cells out after the unit
-                    const bool vote = active && part == 0;
-                    const unsigned grp = __match_any_sync(0xffffffffu, vote ? (int)di : -1 - lane);
-                    if (vote) {
-                        const uint32_t best = __reduce_min_sync(grp, ((uint32_t)cost << 6) | (uint32_t)mode);
-                        if (lane == __ffs(grp) - 1) atomicMin(&s_dec[di - ordBeg], best);
-                    }
+            if (g_cost) g_cost[o] = active ? cost : -1;
+            if (g_sad) { g_sad[o] = active ? sad : -1; g_satd[o] = active ? satd : -1; }   // both or neither (launch_costs)
+        }
+        if (g_best_mode) {
+            // decision = argmin over the CU's modes, lowest mode wins ties: min of (cost << 6 | mode), cost < 2^24.
+            // The lanes of one CU are first reduced in registers (MATCH.ANY + REDUX.MIN), then one lane per CU does the
+            // shared-memory atomicMin: 3-4 distinct addresses per warp instead of 32 lanes serialising on them.
+            const bool vote = inRange && part == 0 && active;
+            const uint32_t key = ((uint32_t)min(2 * sad, satd) << 6) | (uint32_t)mode;
+            const int modes = ty.modes;
+            if (modes >= 16) {
+                // 16 or 32 modes: a CU is exactly one half or one whole warp task (in range, active and voting as a whole),
+                // so its group is known without MATCH and its slot has a single writer: a plain store
+                const unsigned grp = modes == 32 ? 0xffffffffu : ((lane & 16) ? 0xffff0000u : 0x0000ffffu);
+                if (vote) {
+                    const uint32_t best = __reduce_min_sync(grp, key);
+                    if ((lane & (modes - 1)) == 0) s_dec[slot - ordBeg] = best;
+                }
+            } else {
+                const unsigned grp = __match_any_sync(0xffffffffu, vote ? slot : -1 - lane);
+                if (vote) {
+                    const uint32_t best = __reduce_min_sync(grp, key);
+                    if (lane == __ffs(grp) - 1) atomicMin(&s_dec[slot - ordBeg], best);
                 }
             }
-            lr = lr_next;
         }
-        if (g_best_mode && ordCnt > 0) {
-            __syncthreads();
-            for (int i = tid; i < ordCnt; i += NT) {
-                const uint32_t v = s_dec[i];
-                const size_t o = cuBase + c_ord2cu[half][ordBeg + i];
-                g_best_mode[o] = v == 0xffffffffu ? (uint8_t)0xFF : (uint8_t)(v & 63u);
-                g_best_cost[o] = v == 0xffffffffu ? -1 : (int32_t)(v >> 6);
-            }
+        lr = lr_next;
+    }
+    if (g_best_mode) {
+        __syncthreads();
+        const size_t cuBase = (size_t)ctu * MIP_CUS_PER_CTU;
+        for (int i = tid; i < ordCnt; i += NT) {
+            const uint32_t v = s_dec[i];
+            const size_t o = cuBase + c_ord2cu[half][ordBeg + i];
+            g_best_mode[o] = v == 0xffffffffu ? (uint8_t)0xFF : (uint8_t)(v & 63u);
+            g_best_cost[o] = v == 0xffffffffu ? -1 : (int32_t)(v >> 6);
         }
     }
-    // ---- the last CTA to leave puts the scheduler words back to zero for the next launch on this stream
-    if (tid == 0) {
-        __threadfence();
-        s_asg[0] = atomicAdd(sched + SCH_DONE, 1) == (int)gridDim.x - 1;
-    }
-    __syncthreads();
-    if (s_asg[0])
-        for (int i = tid; i < SCH_HALF0 + halves; i += NT) sched[i] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -982,27 +910,28 @@ mip_topk_kernel(const int32_t* __restrict__ cost, int n_ctus, int k, uint8_t* __
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
-static int g_sm_count[64] = {0};
-
-cudaError_t kernels_init(int chunks, const double* weights) {
-    if (chunks < 1) chunks = 1;
-    if (chunks > MAX_CHUNKS) chunks = MAX_CHUNKS;
-    // cum[k] = share of the own part's cost that lies before own unit k (equal shares unless weights are given)
-    double cum[MAX_CHUNKS + 1], wsum = 0;
-    for (int k = 0; k < chunks; ++k) wsum += weights ? weights[k] : 1.0;
-    cum[0] = 0;
-    for (int k = 0; k < chunks; ++k) cum[k + 1] = cum[k] + (weights ? weights[k] : 1.0) / wsum;
+cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
+    // cum[sp][k] = share of a half's cost that lies before chunk k of split sp (equal shares unless weights are given)
+    double cum[2][MAX_CHUNKS + 1];
+    int chunks_of[2];
+    for (int sp = 0; sp < 2; ++sp) {
+        const int chunks = chunks_of[sp] = std::min(std::max(nchunks[sp], 1), MAX_CHUNKS);
+        double wsum = 0;
+        for (int k = 0; k < chunks; ++k) wsum += weights[sp] ? weights[sp][k] : 1.0;
+        cum[sp][0] = 0;
+        for (int k = 0; k < chunks; ++k) cum[sp][k + 1] = cum[sp][k] + (weights[sp] ? weights[sp][k] : 1.0) / wsum;
+    }
     cudaError_t err;
     // CU tables
     DevType types[MIP_NUM_TYPES];
     memset(types, 0, sizeof(types));
+    std::vector<uint32_t> work[2];
     std::vector<uint2> lanes[2];          // 32 lane records per warp task
     std::vector<double> wcost[2];
-    std::vector<char> cut_ok[2];          // may an own unit end after this warp task? (no CU's modes may be split)
-    std::vector<int> ord_after[2];        // 12-mode CUs completed after this warp task (valid where cut_ok)
-    static uint16_t ord2cu[2][DEC_MAX];
-    int ord_total[2] = {0, 0}, own_tasks[2] = {0, 0};
-    bool tail_started = false;
+    std::vector<char> cut_ok[2];          // may a chunk boundary follow this warp task? (no CU's modes may be split)
+    std::vector<int> ord_after[2];        // CU ordinal reached after this warp task (valid where cut_ok)
+    static uint16_t ord2cu[2][2700];
+    int ord_total[2] = {0, 0};
     for (int t = 0; t < MIP_NUM_TYPES; ++t) {
         const mip_cu_type_t& s = MIP_TYPES[t];
         DevType& d = types[t];
@@ -1010,9 +939,6 @@ cudaError_t kernels_init(int chunks, const double* weights) {
         d.shape = (uint8_t)shape_of(s.w, s.h);
         d.cost_off = s.cost_off; d.cu_off = s.cu_off;
         d.parts_log2 = (s.w == 64 && s.h == 64) ? 2 : 0;
-        const bool cell = s.modes < 16;       // decisions merged in shared-memory cells: the own part of the list
-        if (cell && tail_started) return cudaErrorInvalidValue;      // the type table lists the 12-mode types first
-        if (!cell) tail_started = true;
         // CUs per CTU half: CU order is raster, so each half is one contiguous run; no CU crosses y = 64
         for (int hf = 0; hf < 2; ++hf) {
             int first = -1, cnt = 0;
@@ -1025,7 +951,6 @@ cudaError_t kernels_init(int chunks, const double* weights) {
             const double mv = s.size_id == 2 ? 700.0 : (s.size_id == 1 ? 200.0 : 120.0);
             const double c = (mv + 11.0 * s.w * s.h + 2.0 * (s.w + s.h) + 60.0) / (1 << d.parts_log2) + (d.parts_log2 ? mv : 0.0);
             const int per_cu = s.modes << d.parts_log2, ntask = cnt * per_cu;
-            if (!cell && 32 % per_cu != 0) return cudaErrorInvalidValue;       // a 16- or 32-mode CU never straddles warp tasks
             const int nw = (ntask + 31) / 32;
             for (int w = 0; w < nw; ++w) {
                 for (int lane = 0; lane < 32; ++lane) {
@@ -1033,48 +958,48 @@ cudaError_t kernels_init(int chunks, const double* weights) {
                     const int part = tcl & ((1 << d.parts_log2) - 1), cm = tcl >> d.parts_log2;
                     const int cu_local = cm / s.modes, mode = cm % s.modes, cu = first_cu + cu_local;
                     const int cx = s.xs[cu % s.cols], cy = s.ys[cu / s.cols] - hf * TILE_ROWS;
-                    const uint32_t coff = s.cost_off + (uint32_t)cu * s.modes + mode;
-                    const uint32_t di = cell ? (uint32_t)(ord_total[hf] + cu_local) : (uint32_t)(s.cu_off + cu);
-                    if (cx > 127 || cy < 0 || cy > 63 || mode > 31 || part > 3 || coff >= (1u << 17) || di >= (1u << 13)) return cudaErrorInvalidValue;
+                    const uint32_t coff = s.cost_off + (uint32_t)cu * s.modes + mode, slot = (uint32_t)(ord_total[hf] + cu_local);
+                    if (cx > 127 || cy < 0 || cy > 63 || mode > 31 || part > 3 || coff >= (1u << 17) || slot >= (1u << 12)) return cudaErrorInvalidValue;
                     lanes[hf].push_back(make_uint2((uint32_t)cx | ((uint32_t)cy << 7) | ((uint32_t)mode << 13) | ((uint32_t)part << 18) | ((uint32_t)in_range << 20) | ((uint32_t)t << 21),
-                                                   coff | (di << 17)));
+                                                   coff | (slot << 17)));
                 }
+                work[hf].push_back((uint32_t)t | ((uint32_t)w << 8));
                 wcost[hf].push_back(c);
                 const int done = std::min(ntask, 32 * (w + 1));
                 cut_ok[hf].push_back(done % per_cu == 0);
-                ord_after[hf].push_back(ord_total[hf] + (cell ? done / per_cu : 0));
+                ord_after[hf].push_back(ord_total[hf] + done / per_cu);
             }
-            if (cell) {
-                if (ord_total[hf] + cnt > DEC_MAX) return cudaErrorInvalidValue;
-                for (int k = 0; k < cnt; ++k) ord2cu[hf][ord_total[hf] + k] = (uint16_t)(s.cu_off + first_cu + k);
-                ord_total[hf] += cnt;
-                own_tasks[hf] += nw;
-            }
+            for (int k = 0; k < cnt; ++k) ord2cu[hf][ord_total[hf] + k] = (uint16_t)(s.cu_off + first_cu + k);
+            ord_total[hf] += cnt;
+            if (ord_total[hf] > 2700) return cudaErrorInvalidValue;
         }
     }
-    // contiguous, cost-balanced partition of each half's own part into `chunks` own units; the tail follows
-    int begin[2][MAX_CHUNKS + 1], ntasks[2];
-    uint16_t chunk_ord[2][MAX_CHUNKS + 1];
-    for (int hf = 0; hf < 2; ++hf) {
-        ntasks[hf] = (int)wcost[hf].size();
-        if (ntasks[hf] > MAX_WORK) return cudaErrorInvalidValue;
-        double total = 0;
-        for (int i = 0; i < own_tasks[hf]; ++i) total += wcost[hf][i];
-        begin[hf][0] = 0;
-        double acc = 0;
-        int k = 1;
-        chunk_ord[hf][0] = 0;
-        for (int i = 0; i < own_tasks[hf] && k < chunks; ++i) {
-            acc += wcost[hf][i];
-            if (acc >= total * cum[k] && cut_ok[hf][i]) { chunk_ord[hf][k] = (uint16_t)ord_after[hf][i]; begin[hf][k++] = i + 1; }
+    // contiguous, cost-balanced partition of each half's work list into chunks, once per split
+    static int begin[2][2][MAX_CHUNKS + 1];
+    static uint16_t chunk_ord[2][2][MAX_CHUNKS + 1];
+    for (int sp = 0; sp < 2; ++sp)
+        for (int hf = 0; hf < 2; ++hf) {
+            const int chunks = chunks_of[sp];
+            if ((int)work[hf].size() > MAX_WORK) return cudaErrorInvalidValue;
+            double total = 0;
+            for (double c : wcost[hf]) total += c;
+            begin[sp][hf][0] = 0;
+            double acc = 0;
+            int k = 1;
+            chunk_ord[sp][hf][0] = 0;
+            for (size_t i = 0; i < work[hf].size() && k < chunks; ++i) {
+                acc += wcost[hf][i];
+                if (acc >= total * cum[sp][k] && cut_ok[hf][i]) { chunk_ord[sp][hf][k] = (uint16_t)ord_after[hf][i]; begin[sp][hf][k++] = (int)i + 1; }
+            }
+            while (k <= MAX_CHUNKS) { chunk_ord[sp][hf][k] = (uint16_t)ord_total[hf]; begin[sp][hf][k++] = (int)work[hf].size(); }
+            for (int q = 0; q < chunks; ++q)
+                if (chunk_ord[sp][hf][q + 1] - chunk_ord[sp][hf][q] > DEC_MAX) return cudaErrorInvalidValue;   // use more chunks
         }
-        while (k <= MAX_CHUNKS) { chunk_ord[hf][k] = (uint16_t)ord_total[hf]; begin[hf][k++] = own_tasks[hf]; }
-    }
     if ((err = cudaMemcpyToSymbol(c_types, types, sizeof(types))) != cudaSuccess) return err;
     for (int hf = 0; hf < 2; ++hf)
         if ((err = cudaMemcpyToSymbol(g_lane, lanes[hf].data(), lanes[hf].size() * sizeof(uint2), (size_t)hf * MAX_WORK * 32 * sizeof(uint2))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_chunk_begin, begin, sizeof(begin))) != cudaSuccess) return err;
-    if ((err = cudaMemcpyToSymbol(c_tasks, ntasks, sizeof(ntasks))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_chunks, chunks_of, sizeof(chunks_of))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_chunk_ord, chunk_ord, sizeof(chunk_ord))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_ord2cu, ord2cu, sizeof(ord2cu))) != cudaSuccess) return err;
     // matrices: (coef - 32) as signed bytes in the padded shared-memory layout
@@ -1115,23 +1040,13 @@ cudaError_t kernels_init(int chunks, const double* weights) {
     if ((err = cudaFuncSetAttribute(mip_cost_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return err;
     int ctas = 0;
     if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, mip_cost_kernel, NT, SM_TOTAL)) != cudaSuccess) return err;
-    if (getenv("MIPB200_VERBOSE")) fprintf(stderr, "mipb200: cost kernel %d threads, %d B smem, %d CTA(s)/SM, %d chunks per CTU half\n", NT, SM_TOTAL, ctas, chunks);
-    g_chunks = chunks;
-    int dev = 0;
-    if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
-    if (dev >= 0 && dev < 64 && (err = cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
+    if (getenv("MIPB200_VERBOSE")) fprintf(stderr, "mipb200: cost kernel %d threads, %d B smem, %d CTA(s)/SM, %d / %d chunks per CTU half (throughput / lone frame)\n", NT, SM_TOTAL, ctas, chunks_of[0], chunks_of[1]);
+    g_chunks[0] = chunks_of[0];
+    g_chunks[1] = chunks_of[1];
     return cudaSuccess;
 }
 
-// scheduler words of the launches on one stream: 3 + one per CTU half, zero between launches (the kernel leaves them so)
-cudaError_t sched_alloc(int W, int H, int** d_sched) {
-    const size_t n = SCH_HALF0 + (size_t)2 * ((W + 127) >> 7) * ((H + 127) >> 7);
-    cudaError_t e = cudaMalloc((void**)d_sched, n * sizeof(int));
-    if (e != cudaSuccess) return e;
-    return cudaMemset(*d_sched, 0, n * sizeof(int));
-}
-
-int kernels_chunks_per_ctu() { return g_chunks; }
+int kernels_chunks_per_ctu() { return g_chunks[0]; }
 
 // cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no -lcuda at link time)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1206,8 +1121,7 @@ cudaError_t make_filter_params(int ft, int kidx, int bit_depth, FilterParams* fp
 }
 
 cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, int bit_depth, const FilterParams& fp, int32_t* d_cost, int32_t* d_sad,
-                         int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, int* d_sched, cudaStream_t st) {
-    if (!d_sched) return cudaErrorInvalidValue;
+                         int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, bool lone_frame, cudaStream_t st) {
     if (bit_depth != 8 && bit_depth != 10 && bit_depth != 12) return cudaErrorInvalidValue;
     if ((d_best_mode == nullptr) != (d_best_cost == nullptr) || (d_sad == nullptr) != (d_satd == nullptr)) return cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(d_frame) & 15) != 0) return cudaErrorMisalignedAddress;   // TMA needs a 16-byte aligned frame
@@ -1215,11 +1129,8 @@ cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, int bit_depth, c
     cudaError_t e = make_frame_map(d_frame, W, H, &map);
     if (e != cudaSuccess) return e;
     const int nctu = ((W + 127) >> 7) * ((H + 127) >> 7);
-    int dev = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-    const int slots = 2 * (dev >= 0 && dev < 64 && g_sm_count[dev] ? g_sm_count[dev] : 148);     // 2 CTAs per SM are resident
-    const int grid = std::min(slots, (g_chunks + 1) * 2 * nctu);          // persistent CTAs; small frames: one per unit of work
-    mip_cost_kernel<<<grid, NT, SM_TOTAL, st>>>(map, fp, W, H, g_chunks, (1 << bit_depth) - 1, d_cost, d_sad, d_satd, d_best_mode, d_best_cost, d_sched);
+    const int split = lone_frame ? 1 : 0;
+    mip_cost_kernel<<<nctu * 2 * g_chunks[split], NT, SM_TOTAL, st>>>(map, fp, W, H, split, (1 << bit_depth) - 1, d_cost, d_sad, d_satd, d_best_mode, d_best_cost);
     return cudaGetLastError();
 }
 

@@ -6,9 +6,10 @@
 namespace mipb200 {
 
 // One-time per device: packs the MIP matrices, the CU tables and the work list into device memory.
-// chunks = own units per CTU half (the 12-mode part of a half's task list is cut into that many pieces, see the kernel);
-// weights (optional, `chunks` entries) = relative cost share of each piece.
-cudaError_t kernels_init(int chunks_per_half, const double* weights = nullptr);
+// Two splits of a CTU half's work into chunks (= CTAs): [0] used when frames overlap on the GPU, [1] for a lone frame.
+// nchunks[sp] = chunks per half, weights[sp] (may be null: equal) = relative cost share of each chunk, in launch order.
+// cudaErrorInvalidValue: a chunk would hold more CUs than the shared-memory decision table (use more chunks).
+cudaError_t kernels_init(const int* nchunks, const double* const* weights);
 int kernels_chunks_per_ctu();
 
 // Low-pass filter of the fused path, prepared once per engine and passed to the kernel by value (constant-bank
@@ -30,10 +31,9 @@ cudaError_t make_filter_params(int filter_type, int kernel_idx, int bit_depth, F
 // d_best_mode/d_best_cost (both or neither): per-CU argmin over the modes, produced by the same kernel.
 // d_cost may be null when only the decisions are wanted.
 // bit_depth: 10 = the reference (clamp 1023, default sample 512: intra.cl:61, 446, 482); 8 and 12 scale those constants.
-// d_sched: scheduler words from sched_alloc() for this frame size; launches that share them must be ordered (one stream).
+// lone_frame: nothing else will share the GPU with this launch -> the split with the short tail (see kernels_init).
 cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, int bit_depth, const FilterParams& fp, int32_t* d_cost,
-                         int32_t* d_sad, int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, int* d_sched, cudaStream_t st);
-cudaError_t sched_alloc(int W, int H, int** d_sched);
+                         int32_t* d_sad, int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, bool lone_frame, cudaStream_t st);
 
 // Low-pass filter of a whole frame (alternative samples), filter_type 1..8.
 cudaError_t launch_filter(const uint16_t* d_in, uint16_t* d_out, int W, int H, int filter_type, int kernel_idx,

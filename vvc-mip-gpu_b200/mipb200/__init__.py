@@ -28,11 +28,12 @@ EMIT_COSTS = 1
 EMIT_SAD_SATD = 2
 EMIT_DECISIONS = 4
 TOPK_MAX = 12
+LAUNCH_AUTO, LAUNCH_THROUGHPUT, LAUNCH_LATENCY = 0, 1, 2
 
 # every symbol include/mipb200.h declares (tests/test_abi.py checks the header against this)
 ABI_SYMBOLS = (
     "mipb200_create", "mipb200_destroy", "mipb200_next_input", "mipb200_submit", "mipb200_collect",
-    "mipb200_in_flight", "mipb200_num_ctus", "mipb200_device_count", "mipb200_run_device", "mipb200_filter_device",
+    "mipb200_in_flight", "mipb200_set_launch_mode", "mipb200_num_ctus", "mipb200_device_count", "mipb200_run_device", "mipb200_filter_device",
     "mipb200_decide_device", "mipb200_topk_device", "mipb200_kernel_launches", "mipb200_device_energy_mj", "mipb200_pin_host", "mipb200_pin_host_on", "mipb200_unpin_host", "mipb200_sync", "mipb200_last_error",
     "mipb200_version",
 )
@@ -94,6 +95,8 @@ def lib() -> ctypes.CDLL:
         L.mipb200_collect.restype = ctypes.c_int
         L.mipb200_in_flight.argtypes = [vp]
         L.mipb200_in_flight.restype = ctypes.c_int
+        L.mipb200_set_launch_mode.argtypes = [vp, ctypes.c_int]
+        L.mipb200_set_launch_mode.restype = ctypes.c_int
         L.mipb200_num_ctus.argtypes = [ctypes.c_int, ctypes.c_int]
         L.mipb200_num_ctus.restype = ctypes.c_int
         L.mipb200_device_count.argtypes = []
@@ -223,6 +226,10 @@ class Engine:
 
     def in_flight(self) -> int:
         return lib().mipb200_in_flight(self._h)
+
+    def set_launch_mode(self, mode: int) -> None:
+        """LAUNCH_AUTO / LAUNCH_THROUGHPUT / LAUNCH_LATENCY: how a frame is cut into thread blocks (see include/mipb200.h)."""
+        _check(lib().mipb200_set_launch_mode(self._h, mode))
 
     def run(self, frame: np.ndarray) -> FrameResult:
         self.submit(np.ascontiguousarray(frame, dtype=np.uint16))
