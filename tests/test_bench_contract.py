@@ -48,4 +48,7 @@ def test_gpu_arm_json_line():
     rf = line["roofline"]
     assert set(rf) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and rf["bound"] == "int32" and 0.3 < rf["frac"] < 1.0
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and set(rf["hbm"]) >= {"achieved", "peak", "unit", "frac"}
+    assert 0.3 < rf["lone_frame"]["frac"] <= rf["frac"] * 1.02 and rf["traffic"] > rf["hbm"]["algorithmic_bytes_per_launch"]
+    assert line["shard_check"]["status"] == "ok" and len(line["sizes"]) == 2 and all(s["value"] > 50 for s in line["sizes"])
+    assert line["e2e_like_for_like"]["value"] == line["e2e_costs"]["value"] > 300
     assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"} and "workload" in line["config"]
