@@ -15,6 +15,7 @@ hot path (filter -> MIP costs -> decisions) over a batch of B distinct frames pe
          the MIP decisions (best mode + its cost for every CU); e2e_costs additionally reads back the
          full int32 cost table (the reference's minSadHad readback, 52.8 MB per 1080p frame) and is
          repeated as e2e_like_for_like: the result the reference arm's e2e returns
+         e2e_costs_compact: the same table in the lossless compact transport (71 % of the bytes)
   sizes  the same three numbers for BASELINE configs 4 (3840x2160, original samples) and 5 (7680x4320,
          alternative samples) at the current GPU count
   shard_check   N > 1: every rank runs its poc % N share of a fixed 16-frame set, the decision hashes are
@@ -427,12 +428,14 @@ def main():
     kernel_ms = wl.kernel_alone(max(16, min(96, args.steps * B)))
     e2e_dec_s = wl.host_path(emit_dec, False, e2e_steps)
     e2e_s = wl.host_path(emit_full, True, e2e_steps)
+    e2e_cmp_s = wl.host_path(mipb200.EMIT_COSTS_COMPACT | mipb200.EMIT_DECISIONS, False, e2e_steps)
     pool_np = wl.pool_np
     wl.free()
-    dev_ms, e2e_ms, e2e_dec_ms, kernel_ms = max_over_ranks([dev_ms, e2e_s * 1e3, e2e_dec_s * 1e3, kernel_ms])
+    dev_ms, e2e_ms, e2e_dec_ms, kernel_ms, e2e_cmp_ms = max_over_ranks([dev_ms, e2e_s * 1e3, e2e_dec_s * 1e3, kernel_ms, e2e_cmp_s * 1e3])
     value = B * args.steps * world / (dev_ms * 1e-3)
     e2e_fps = B * e2e_steps * world / (e2e_ms * 1e-3)
     e2e_dec_fps = B * e2e_steps * world / (e2e_dec_ms * 1e-3)
+    e2e_cmp_fps = B * e2e_steps * world / (e2e_cmp_ms * 1e-3)
 
     # ---------------- BASELINE configs 4 and 5 at this GPU count ----------------
     int32_peak, int32_src = _int32_peak()
@@ -480,6 +483,10 @@ def main():
             "e2e_costs": e2e_costs,
             # full table against full table: what the reference arm's e2e returns (there as 64-bit integers)
             "e2e_like_for_like": dict(e2e_costs, compare_with="the reference arm's e2e / e2e_overlapped (full minSadHad table on the host)"),
+            # the same table in the compact transport (uint16 for CUs of <= 32 samples, lossless): what the link allows then
+            "e2e_costs_compact": {"value": e2e_cmp_fps, "unit": "frames/s", "h2d_bytes_per_step": B * frame_bytes,
+                                  "d2h_bytes_per_step": B * (mipb200.COMPACT_BYTES_PER_CTU * g["n_ctus"] + 5 * g["n_ctus"] * CUS_PER_CTU),
+                                  "result": "decisions + the compact cost table (MIPB200_EMIT_COSTS_COMPACT: 276 672 instead of 391 360 bytes per CTU; mipb200_expand_costs() restores int32)"},
             "sizes": sizes,
             "shard_check": shard,
             "gpu_launches": launches,

@@ -44,6 +44,13 @@ extern "C" {
 #define MIPB200_EMIT_COSTS 1u      /* int32 cost[nCTU][97840] = min(2*SAD, SATD), reference order */
 #define MIPB200_EMIT_SAD_SATD 2u   /* int32 sad[...] and satd[...] in the same layout */
 #define MIPB200_EMIT_DECISIONS 4u  /* uint8 best_mode[nCTU][5380] + int32 best_cost[nCTU][5380] */
+#define MIPB200_EMIT_COSTS_COMPACT 8u /* instead of MIPB200_EMIT_COSTS: the same table, same order, 71 % of the bytes -- the
+                                        costs of CU types of at most 32 samples (4x4, 8x4, 4x8) as uint16 (<= 65 472 by
+                                        construction with samples of up to 10 bits; 0xFFFF = skipped), all others int32:
+                                        mipb200_compact_bytes_per_ctu() = 276 672 bytes per CTU, mipb200_expand_costs()
+                                        turns it into the int32 table.  The full-table rate is bound by the host link
+                                        (56 MB per 1080p frame), so this is 1.4x the frames/s.  Not with bit_depth 12,
+                                        MIPB200_EMIT_SAD_SATD or top_k > 1. */
 
 /* filter_type: 0 = original samples (USE_ALTERNATIVE_SAMPLES 0, main.cpp:10);
  * 1..8 = the reference's availableFilters in order (constants.h:25-34):
@@ -85,6 +92,7 @@ typedef struct mipb200_result {
     int top_k;                /* entries per CU in the two arrays below (0 when not requested) */
     const uint8_t* topk_mode; /* [n_ctus][5380][top_k]; ascending (cost, mode); 0xFF if skipped */
     const int32_t* topk_cost; /* [n_ctus][5380][top_k] */
+    const void* cost_compact; /* [n_ctus][mipb200_compact_bytes_per_ctu()] with MIPB200_EMIT_COSTS_COMPACT (then cost is NULL) */
 } mipb200_result;
 
 /* Replaces the OpenCL platform/context/queue/buffer/program setup, main.cpp:87-315, 408-549. */
@@ -152,6 +160,12 @@ int mipb200_decide_device(mipb200_engine* e, const int32_t* d_cost, uint8_t* d_b
  * entry 0 equals mipb200_decide_device()'s answer.  No reference counterpart: the reference stops at the cost log
  * (main_aux_functions.h:735-798) and leaves the ranking to the consumer. */
 int mipb200_topk_device(mipb200_engine* e, const int32_t* d_cost, int k, uint8_t* d_modes, int32_t* d_costs, void* stream);
+
+/* Compact cost table -> int32 table (cost[n_ctus][97840], -1 for skipped CUs), on the host, with up to `threads` threads.
+ * Layout of a CTU's compact record: the 47 type blocks in table order; a block holds modes * CUs entries in the order of the
+ * int32 table; entries are uint16 when the type's CUs have at most 32 samples, int32 otherwise (csrc/mip_compact.h). */
+size_t mipb200_compact_bytes_per_ctu(void);
+int mipb200_expand_costs(const void* compact, int n_ctus, int32_t* cost, int threads);
 
 /* Number of this library's kernels launched so far on this engine (bench.py: gpu_launches). */
 long long mipb200_kernel_launches(const mipb200_engine* e);

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/mipb200.h"
+#include "../../vvc-mip-gpu_b200/csrc/mip_compact.h"
 
 extern "C" {
 int mipo_set_bit_depth(int bits);
@@ -38,7 +39,7 @@ struct mipb200_engine {
     std::deque<Frame> fifo;
     std::vector<uint16_t> input;
     std::vector<int32_t> cost, sad, satd, best_cost, topk_cost;
-    std::vector<uint8_t> best_mode, topk_mode;
+    std::vector<uint8_t> best_mode, topk_mode, compact;
 };
 
 #define MOCK_API extern "C" __attribute__((visibility("default")))
@@ -111,6 +112,12 @@ MOCK_API int mipb200_collect(mipb200_engine* e, mipb200_result* r) {
             }
     }
     const unsigned em = e->cfg.emit;
+    r->cost_compact = nullptr;
+    if (em & MIPB200_EMIT_COSTS_COMPACT) {
+        e->compact.resize((size_t)e->n_ctus * MIP_COMPACT_BYTES_PER_CTU);
+        if (mip_compact_pack(e->cost.data(), e->compact.data(), e->n_ctus) != 0) { strcpy(g_err, "mock: a narrow cost does not fit 16 bits"); return MIPB200_EINVAL; }
+        r->cost_compact = e->compact.data();
+    }
     r->poc = f.poc;
     r->n_ctus = e->n_ctus;
     r->cost = (em & MIPB200_EMIT_COSTS) ? e->cost.data() : nullptr;

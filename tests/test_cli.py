@@ -320,3 +320,21 @@ def test_cli_rejects_samples_beyond_the_bit_depth(mip, tmp_path):
     f.astype("<u2").tofile(str(raw))
     r = _run(mip, "-f", "1", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog")
     assert r.returncode == 1 and "does not fit 10 bits" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_compact_log(mip, oracle, tmp_path):
+    """--CompactLog on the GPU: every frame's compact table at its POC offset; expanded it equals the oracle's int32 table."""
+    from mipb200 import frames
+    W, H, N = 384, 200, 4
+    fs = [frames.noise_frame(W, H, 700 + i) for i in range(N)]
+    raw = tmp_path / "in.u16"
+    np.stack(fs).astype("<u2").tofile(str(raw))
+    dump = tmp_path / "c.cmp"
+    r = _run(mip, "-f", str(N), "-s", f"{W}x{H}", "-o", str(raw), "--InputFormat=u16", "--NoLog", f"--CompactLog={dump}", "--StageStamps=0",
+             "--UseAlternativeSamples=1", "--FilterType=filterFrame_1d_float", "--KernelIdx=4")
+    assert r.returncode == 0, r.stdout + r.stderr
+    hdr, rec = frames.read_compact_dump(str(dump))
+    assert hdr["frames"] == N and hdr["bytes_per_ctu"] == mip.COMPACT_BYTES_PER_CTU and hdr["filter_type"] == 2
+    for poc in range(N):
+        assert np.array_equal(mip.expand_costs(rec[poc]), oracle.run_frame(fs[poc], 2, 4)), poc

@@ -208,3 +208,21 @@ def test_streamed_csv_input_and_all_frames_logs(mock_cli, oracle, tmp_path):
     # a short CSV is still an error, reported with the line count
     r = mock_cli("-f", str(N + 1), "-s", f"{W}x{H}", "-o", str(csv), "--RingFrames=2", "--NoLog")
     assert r.returncode == 1 and f"holds {N * H} lines, need {(N + 1) * H}" in r.stderr
+
+
+def test_compact_log(mock_cli, oracle, tmp_path, mip):
+    """--CompactLog: the compact table of every frame at its POC offset; expanded (mipb200_expand_costs) it is the int32 table."""
+    W, H, N = 136, 72, 3
+    fs = [frames.natural_frame(W, H, 20 + i) for i in range(N)]
+    raw = tmp_path / "in.u16"
+    np.stack(fs).astype("<u2").tofile(str(raw))
+    dump, dig = tmp_path / "c.cmp", tmp_path / "d.csv"
+    r = mock_cli("-f", str(N), "-s", f"{W}x{H}", "-o", str(raw), "--InputFormat=u16", "--NoLog", f"--CompactLog={dump}", f"--Digest={dig}", "--NumGpus=2", gpus=2)
+    assert r.returncode == 0, r.stdout + r.stderr
+    hdr, rec = frames.read_compact_dump(str(dump))
+    assert hdr["frames"] == N and hdr["n_ctus"] == 2 and hdr["bytes_per_ctu"] == mip.COMPACT_BYTES_PER_CTU == 276672
+    for poc in range(N):
+        assert np.array_equal(mip.expand_costs(rec[poc], threads=2), oracle.run_frame(fs[poc])), poc
+    assert open(dig).read().splitlines()[0] == "POC,CostsCompact,Modes,BestCosts"
+    r = mock_cli("-f", "1", "-s", f"{W}x{H}", "-o", str(raw), "--InputFormat=u16", f"--CompactLog={dump}")
+    assert r.returncode == 1 and "CompactLog needs --NoLog" in r.stdout

@@ -201,3 +201,28 @@ def test_launch_modes_give_identical_results(mip, oracle):
     with pytest.raises(mip.MipError):
         with mip.Engine(W, H, slots=1) as eng:
             eng.set_launch_mode(7)
+
+
+@pytest.mark.parametrize("ft,kidx", [(0, 0), (8, 2)])
+def test_compact_cost_table(mip, oracle, ft, kidx):
+    """MIPB200_EMIT_COSTS_COMPACT: 71 % of the bytes, nothing lost -- expanded it equals the int32 table, for noise (the
+    largest costs a 10-bit frame can produce in the 16-bit entries), extremes and a frame with partial CTUs."""
+    from mipb200 import frames
+    W, H = 384, 200
+    fs = [frames.noise_frame(W, H, 61), frames.extreme_frame(W, H, 2), frames.natural_frame(W, H, 62)]
+    with mip.Engine(W, H, filter_type=ft, kernel_idx=kidx, slots=3, emit=mip.EMIT_COSTS_COMPACT | mip.EMIT_DECISIONS) as eng:
+        for i, f in enumerate(fs):
+            eng.submit(f, i)
+        for i, f in enumerate(fs):
+            r = eng.collect()
+            want = oracle.run_frame(f, ft, kidx)
+            assert r.cost is None and r.cost_compact.shape == (eng.n_ctus, mip.COMPACT_BYTES_PER_CTU)
+            assert np.array_equal(r.expand_costs(threads=3), want), i
+            bm, bc = oracle.decisions(want)
+            assert np.array_equal(r.best_mode, bm) and np.array_equal(r.best_cost, bc)
+    assert mip.lib().mipb200_compact_bytes_per_ctu() == mip.COMPACT_BYTES_PER_CTU
+    for kw in (dict(emit=mip.EMIT_COSTS_COMPACT | mip.EMIT_COSTS), dict(emit=mip.EMIT_COSTS_COMPACT, bit_depth=12),
+               dict(emit=mip.EMIT_COSTS_COMPACT | mip.EMIT_DECISIONS, top_k=3), dict(emit=mip.EMIT_COSTS_COMPACT | mip.EMIT_SAD_SATD)):
+        with pytest.raises(mip.MipError) as ei:
+            mip.Engine(W, H, **kw)
+        assert ei.value.code == -1

@@ -50,6 +50,7 @@
 #include <vector>
 
 #include "../../include/mipb200.h"
+#include "mip_compact.h"
 #include "mip_tables.h"
 
 #ifndef USE_ALTERNATIVE_SAMPLES
@@ -77,16 +78,16 @@ struct Options {
     int inputFrames = 0;    // frames the input file holds (0: as many as -f); frame poc is file frame poc % inputFrames
     int ringFrames = 0;     // capacity of the page-locked frame ring (0: 2 GiB worth, at least Slots + 1 per GPU)
     int slots = 3;          // frames in flight per engine
-    std::string inputFormat = "csv", decisionsLog, binaryLog, decisionsBin, digest;
+    std::string inputFormat = "csv", decisionsLog, binaryLog, decisionsBin, digest, compactLog;
     bool allFrames = false, compat = false, noLog = false, help = false, energy = false;
 };
 
 const char* kLongOpts[] = {"help", "DeviceIndex", "FramesToBeEncoded", "Resolution", "OriginalFrames", "OutputPreffix",
                            "FilterType", "KernelIdx", "UseAlternativeSamples", "NumGpus", "AllFrames", "Compat", "NoLog",
                            "InputFormat", "DecisionsLog", "TopK", "Energy", "StageStamps", "BitDepth", "BinaryLog", "DecisionsBin", "Digest",
-                           "InputFrames", "RingFrames", "Slots"};
+                           "InputFrames", "RingFrames", "Slots", "CompactLog"};
 const bool kTakesValue[] = {false, true, true, true, true, true, true, true, true, true, false, false, false, true, true,
-                            true, false, true, true, true, true, true, true, true, true};
+                            true, false, true, true, true, true, true, true, true, true, true};
 constexpr int kNumOpts = sizeof(kLongOpts) / sizeof(kLongOpts[0]);
 
 void print_help() {
@@ -105,6 +106,7 @@ void print_help() {
            "  --InputFormat arg (=csv)       csv | u16 (raw little-endian luma) | yuv420p | yuv420p10le\n"
            "  --DecisionsLog arg             write POC,CTU,cuSizeName,W,H,CU,X,Y,BestMode,BestCost for every frame\n"
            "  --BinaryLog arg                write every frame's cost table as raw int32 (64-byte header, see INTEGRATION.md)\n"
+           "  --CompactLog arg               like --BinaryLog with the compact table (uint16 for CUs of <= 32 samples): 71 %% of the bytes\n"
            "  --DecisionsBin arg             write every frame's decisions raw: uint8 modes then int32 costs (64-byte header)\n"
            "  --Digest arg                   write POC,<64-bit hash of each result array> for every frame\n"
            "  --InputFrames arg              frames held by the input file; frame poc reads file frame poc %% arg (default: -f)\n"
@@ -196,6 +198,7 @@ bool parse_args(int argc, char** argv, Options& o) {
             case 22: ok = to_int(val, &o.inputFrames); break;
             case 23: ok = to_int(val, &o.ringFrames); break;
             case 24: ok = to_int(val, &o.slots); break;
+            case 25: o.compactLog = val; break;
         }
         if (!ok) { fprintf(stderr, "the argument ('%s') for option '--%s' is invalid\n", val.c_str(), kLongOpts[opt]); return false; }
     }
@@ -542,7 +545,7 @@ struct Shared {
     std::vector<uint64_t> digCost, digMode, digBest;                // --Digest: one hash per frame and array
     std::atomic<int> errors{0};
     bool stamps = false;
-    int binFd = -1, decFd = -1;                                     // --BinaryLog, --DecisionsBin
+    int binFd = -1, decFd = -1, cmpFd = -1;                         // --BinaryLog, --DecisionsBin, --CompactLog
     OrderedLog costLog, decLog;                                     // --AllFrames text log, --DecisionsLog
 };
 
@@ -590,6 +593,10 @@ bool consume_result(Shared* sh, const mipb200_result& r) {
         perror("error while writing the binary log");   // raw table straight from the pinned ring to its place in the file
         return false;
     }
+    if (sh->cmpFd >= 0) {
+        const size_t rec = (size_t)sh->nCtus * MIP_COMPACT_BYTES_PER_CTU;
+        if (!pwrite_all(sh->cmpFd, r.cost_compact, rec, (off_t)kBinHeader + (off_t)poc * (off_t)rec)) { perror("error while writing the compact log"); return false; }
+    }
     if (sh->decFd >= 0) {   // frame record: modes [nCTU][5380][k] uint8, then costs [nCTU][5380][k] int32
         const off_t rec = (off_t)(ncu * 5), off = (off_t)kBinHeader + (off_t)poc * rec;
         if (!pwrite_all(sh->decFd, bm, ncu, off) || !pwrite_all(sh->decFd, bc, ncu * sizeof(int32_t), off + (off_t)ncu)) {
@@ -599,6 +606,7 @@ bool consume_result(Shared* sh, const mipb200_result& r) {
     }
     if (!o.digest.empty()) {
         if (r.cost) sh->digCost[poc] = digest64(r.cost, ncost * sizeof(int32_t));
+        if (r.cost_compact) sh->digCost[poc] = digest64(r.cost_compact, (size_t)sh->nCtus * MIP_COMPACT_BYTES_PER_CTU);
         if (bm) { sh->digMode[poc] = digest64(bm, ncu); sh->digBest[poc] = digest64(bc, ncu * sizeof(int32_t)); }
     }
     if (!o.noLog && !o.allFrames && poc == 0) {   // the reference exports frame 0 only (main.cpp:1268), after the timed window
@@ -743,8 +751,14 @@ int main(int argc, char** argv) {
     sh.k = o.topK > 1 ? o.topK : 1;
     {
         const bool wantLog = !o.noLog, wantDec = !o.decisionsLog.empty() || !o.decisionsBin.empty(), wantBin = !o.binaryLog.empty();
-        const bool wantCost = wantLog || wantBin || (!wantDec && o.digest.empty());    // nothing else asked for: the reference's table
-        sh.emit = (wantCost ? MIPB200_EMIT_COSTS : 0) | (wantLog && !o.compat ? MIPB200_EMIT_SAD_SATD : 0) | (wantDec || !wantCost || !o.digest.empty() ? MIPB200_EMIT_DECISIONS : 0);
+        const bool wantCmp = !o.compactLog.empty();
+        if (wantCmp && (wantLog || wantBin || o.bitDepth == 12 || o.topK > 1)) {
+            printf("  [!] ERROR: CompactLog needs --NoLog and excludes --BinaryLog, --TopK and --BitDepth=12 (it replaces the int32 table)\n");
+            return 1;
+        }
+        const bool wantCost = wantLog || wantBin || (!wantDec && !wantCmp && o.digest.empty());    // nothing else asked for: the reference's table
+        sh.emit = (wantCost ? MIPB200_EMIT_COSTS : 0) | (wantCmp ? MIPB200_EMIT_COSTS_COMPACT : 0) | (wantLog && !o.compat ? MIPB200_EMIT_SAD_SATD : 0) |
+                  (wantDec || (!wantCost && !wantCmp) || !o.digest.empty() ? MIPB200_EMIT_DECISIONS : 0);
     }
 
     // ---- the frame ring: resident when the distinct frames fit, streamed otherwise
@@ -814,6 +828,7 @@ int main(int argc, char** argv) {
         return fd;
     };
     if (!o.binaryLog.empty() && (sh.binFd = open_bin(o.binaryLog, "MIPB200C", MIP_COSTS_PER_CTU, "error while opening the binary log")) < 0) { destroy_all(); return 1; }
+    if (!o.compactLog.empty() && (sh.cmpFd = open_bin(o.compactLog, "MIPB200K", MIP_COMPACT_BYTES_PER_CTU, "error while opening the compact log")) < 0) { destroy_all(); return 1; }
     if (!o.decisionsBin.empty() && (sh.decFd = open_bin(o.decisionsBin, "MIPB200D", MIP_CUS_PER_CTU, "error while opening the binary decisions")) < 0) { destroy_all(); return 1; }
     if (!o.noLog && o.allFrames) {
         const std::string name = o.prefix + ".csv";
@@ -862,6 +877,7 @@ int main(int argc, char** argv) {
     destroy_all();
     if (sh.binFd >= 0) close(sh.binFd);
     if (sh.decFd >= 0) close(sh.decFd);
+    if (sh.cmpFd >= 0) close(sh.cmpFd);
     if (sh.costLog.f) fclose(sh.costLog.f);
     if (sh.decLog.f) fclose(sh.decLog.f);
     if (ring.pinned) mipb200_unpin_host(ring.base);
@@ -884,8 +900,8 @@ int main(int argc, char** argv) {
     if (!o.digest.empty()) {
         FILE* f = fopen(o.digest.c_str(), "w");
         if (!f) { perror("error while opening the digest file"); return 1; }
-        const bool haveCost = sh.emit & MIPB200_EMIT_COSTS;
-        fprintf(f, "POC,%sModes,BestCosts\n", haveCost ? "Costs," : "");
+        const bool haveCost = sh.emit & (MIPB200_EMIT_COSTS | MIPB200_EMIT_COSTS_COMPACT);
+        fprintf(f, "POC,%sModes,BestCosts\n", (sh.emit & MIPB200_EMIT_COSTS_COMPACT) ? "CostsCompact," : haveCost ? "Costs," : "");
         for (int poc = 0; poc < o.nFrames; ++poc) {
             if (haveCost) fprintf(f, "%d,%016llx,%016llx,%016llx\n", poc, (unsigned long long)sh.digCost[poc], (unsigned long long)sh.digMode[poc], (unsigned long long)sh.digBest[poc]);
             else fprintf(f, "%d,%016llx,%016llx\n", poc, (unsigned long long)sh.digMode[poc], (unsigned long long)sh.digBest[poc]);

@@ -12,11 +12,13 @@
 
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>   // header-only: ranges cost a pointer test unless a profiler (nsys / ncu --nvtx) is attached
 
 #include "../../include/mipb200.h"
+#include "mip_compact.h"
 #include "mip_kernels.h"
 #include "mip_tables.h"
 
@@ -153,7 +155,12 @@ static int check_cfg(const mipb200_config* c) {
                         MIP_FILTER_NAMES[c->filter_type - 1]);
     }
     if (c->slots < 1 || c->slots > 16) return fail(MIPB200_EINVAL, "slots %d out of range 1..16", c->slots);
-    if (c->emit == 0 || (c->emit & ~7u)) return fail(MIPB200_EINVAL, "emit mask 0x%x invalid", c->emit);
+    if (c->emit == 0 || (c->emit & ~15u)) return fail(MIPB200_EINVAL, "emit mask 0x%x invalid", c->emit);
+    if (c->emit & MIPB200_EMIT_COSTS_COMPACT) {
+        if (c->emit & (MIPB200_EMIT_COSTS | MIPB200_EMIT_SAD_SATD)) return fail(MIPB200_EINVAL, "MIPB200_EMIT_COSTS_COMPACT replaces MIPB200_EMIT_COSTS and excludes MIPB200_EMIT_SAD_SATD");
+        if (c->bit_depth == 12) return fail(MIPB200_EINVAL, "the compact cost table holds 16-bit entries: bit_depth 12 needs MIPB200_EMIT_COSTS");
+        if (c->top_k > 1) return fail(MIPB200_EINVAL, "top_k %d reads the int32 table: use MIPB200_EMIT_COSTS", c->top_k);
+    }
     if (c->top_k < 0 || c->top_k > MIPB200_TOPK_MAX) return fail(MIPB200_EINVAL, "top_k %d out of range 0..%d", c->top_k, MIPB200_TOPK_MAX);
     if (c->bit_depth != 0 && c->bit_depth != 8 && c->bit_depth != 10 && c->bit_depth != 12)
         return fail(MIPB200_EINVAL, "bit_depth %d not one of 0 (= 10), 8, 10, 12", c->bit_depth);
@@ -249,7 +256,9 @@ MIPB200_API int mipb200_create(mipb200_engine** out, const mipb200_config* cfg) 
         delete e;
         return fail(MIPB200_EINVAL, "filter parameters of filter_type %d kernel_idx %d failed their exactness check", cfg->filter_type, cfg->kernel_idx);
     }
-    const bool wc = cfg->emit & MIPB200_EMIT_COSTS, ws = cfg->emit & MIPB200_EMIT_SAD_SATD, wd = cfg->emit & MIPB200_EMIT_DECISIONS;
+    const bool wk = cfg->emit & MIPB200_EMIT_COSTS_COMPACT;
+    if (wk) e->cost_bytes = (size_t)e->n_ctus * MIP_COMPACT_BYTES_PER_CTU;      // the one table of this engine is the compact one
+    const bool wc = (cfg->emit & MIPB200_EMIT_COSTS) || wk, ws = cfg->emit & MIPB200_EMIT_SAD_SATD, wd = cfg->emit & MIPB200_EMIT_DECISIONS;
     const int tk = cfg->top_k > 1 ? cfg->top_k : 0;
 #define E_TRY(call)                                                                                     \
     do {                                                                                                \
@@ -337,7 +346,7 @@ MIPB200_API uint16_t* mipb200_next_input(mipb200_engine* e) {
 static int enqueue_kernels(mipb200_engine* e, const uint16_t* d_frame, int32_t* d_cost, int32_t* d_sad,
                            int32_t* d_satd, uint8_t* d_bm, int32_t* d_bc, bool lone, cudaStream_t st) {
     const mipb200_config& c = e->cfg;
-    CU_TRY(mipb200::launch_costs(d_frame, c.width, c.height, c.bit_depth, e->fp, d_cost, d_sad, d_satd, d_bm, d_bc, lone, st));
+    CU_TRY(mipb200::launch_costs(d_frame, c.width, c.height, c.bit_depth, e->fp, d_cost, d_sad, d_satd, d_bm, d_bc, lone, (c.emit & MIPB200_EMIT_COSTS_COMPACT) != 0, st));
     e->launches++;
     return MIPB200_OK;
 }
@@ -412,7 +421,9 @@ MIPB200_API int mipb200_collect(mipb200_engine* e, mipb200_result* out) {
     }
     out->poc = s.poc;
     out->n_ctus = e->n_ctus;
-    out->cost = s.h_cost;
+    const bool wk = e->cfg.emit & MIPB200_EMIT_COSTS_COMPACT;
+    out->cost = wk ? nullptr : s.h_cost;
+    out->cost_compact = wk ? s.h_cost : nullptr;
     out->sad = s.h_sad;
     out->satd = s.h_satd;
     out->best_mode = s.h_best_mode;
@@ -469,6 +480,19 @@ MIPB200_API int mipb200_topk_device(mipb200_engine* e, const int32_t* d_cost, in
     cudaStream_t st = stream ? (cudaStream_t)stream : e->aux_stream;
     CU_TRY(mipb200::launch_topk(d_cost, e->n_ctus, k, d_modes, d_costs, st));
     e->launches++;
+    return MIPB200_OK;
+}
+
+MIPB200_API size_t mipb200_compact_bytes_per_ctu(void) { return MIP_COMPACT_BYTES_PER_CTU; }
+
+MIPB200_API int mipb200_expand_costs(const void* compact, int n_ctus, int32_t* cost, int threads) {
+    if (!compact || !cost || n_ctus < 0) return fail(MIPB200_EINVAL, "compact, cost and a non-negative n_ctus are required");
+    const int nth = std::max(1, std::min(threads, std::min(n_ctus, 64)));
+    if (nth == 1) { mip_compact_expand(compact, cost, 0, n_ctus); return MIPB200_OK; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; ++t)
+        th.emplace_back([=] { mip_compact_expand(compact, cost, (int)((long long)n_ctus * t / nth), (int)((long long)n_ctus * (t + 1) / nth)); });
+    for (auto& x : th) x.join();
     return MIPB200_OK;
 }
 

@@ -35,6 +35,7 @@
 #include <mutex>
 #include <vector>
 
+#include "mip_compact.h"
 #include "mip_filters.h"
 #include "mip_matrices.h"
 #include "mip_tables.h"
@@ -97,8 +98,9 @@ constexpr int MAX_WORK = 1700;          // warp tasks per CTU half
 
 struct DevType {               // what device code needs to know about a CU type; everything positional is in g_lane
     uint8_t w, h, modes, shape;
-    uint8_t parts_log2, pad[3];      // lanes that share one (CU, mode): 4 for 64x64 (a quarter of the strips each), else 1
+    uint8_t parts_log2, narrow, pad[2];   // lanes that share one (CU, mode): 4 for 64x64 (a quarter of the strips each), else 1; narrow: 16-bit entries in the compact table
     uint32_t cost_off, cu_off;       // first cost / first CU of the type inside a CTU
+    uint32_t cmp_off;                // byte offset of the type's block inside a CTU's compact record (mip_compact.h)
 };
 
 __constant__ DevType c_types[MIP_NUM_TYPES];
@@ -616,7 +618,7 @@ __device__ __forceinline__ void build_ref_tile(uint16_t* s_refT, uint16_t* s_ref
 // The fused kernel
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 2)
-mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams fp, int W, int H, int split, int maxv,
+mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams fp, int W, int H, int split, int maxv, int compact,
                 int32_t* __restrict__ g_cost, int32_t* __restrict__ g_sad, int32_t* __restrict__ g_satd,
                 uint8_t* __restrict__ g_best_mode, int32_t* __restrict__ g_best_cost) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -752,7 +754,17 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         if (inRange && part == 0) {
             const uint32_t o = ctuBase + coff;
             const int cost = min(2 * sad, satd);            // intra.cl:1166
-            if (g_cost) g_cost[o] = active ? cost : -1;
+            if (g_cost) {
+                if (!compact) g_cost[o] = active ? cost : -1;
+                else {
+                    // compact table (mip_compact.h): the type's block inside the CTU's record, 16-bit entries for CUs of at
+                    // most 32 samples (cost <= 65 472 with 10-bit samples), int32 otherwise
+                    unsigned char* rec = reinterpret_cast<unsigned char*>(g_cost) + (size_t)ctu * MIP_COMPACT_BYTES_PER_CTU + ty.cmp_off;
+                    const uint32_t idx = coff - ty.cost_off;
+                    if (ty.narrow) reinterpret_cast<uint16_t*>(rec)[idx] = active ? (uint16_t)cost : (uint16_t)0xFFFFu;
+                    else reinterpret_cast<int32_t*>(rec)[idx] = active ? cost : -1;
+                }
+            }
             if (g_sad) { g_sad[o] = active ? sad : -1; g_satd[o] = active ? satd : -1; }   // both or neither (launch_costs)
         }
         if (g_best_mode) {
@@ -939,6 +951,8 @@ cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
         d.shape = (uint8_t)shape_of(s.w, s.h);
         d.cost_off = s.cost_off; d.cu_off = s.cu_off;
         d.parts_log2 = (s.w == 64 && s.h == 64) ? 2 : 0;
+        d.narrow = (uint8_t)mip_compact_narrow(t);
+        d.cmp_off = (uint32_t)mip_compact_type_offset(t);
         // CUs per CTU half: CU order is raster, so each half is one contiguous run; no CU crosses y = 64
         for (int hf = 0; hf < 2; ++hf) {
             int first = -1, cnt = 0;
@@ -995,6 +1009,7 @@ cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
             for (int q = 0; q < chunks; ++q)
                 if (chunk_ord[sp][hf][q + 1] - chunk_ord[sp][hf][q] > DEC_MAX) return cudaErrorInvalidValue;   // use more chunks
         }
+    if (mip_compact_type_offset(MIP_NUM_TYPES) != MIP_COMPACT_BYTES_PER_CTU) return cudaErrorInvalidValue;
     if ((err = cudaMemcpyToSymbol(c_types, types, sizeof(types))) != cudaSuccess) return err;
     for (int hf = 0; hf < 2; ++hf)
         if ((err = cudaMemcpyToSymbol(g_lane, lanes[hf].data(), lanes[hf].size() * sizeof(uint2), (size_t)hf * MAX_WORK * 32 * sizeof(uint2))) != cudaSuccess) return err;
@@ -1121,7 +1136,8 @@ cudaError_t make_filter_params(int ft, int kidx, int bit_depth, FilterParams* fp
 }
 
 cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, int bit_depth, const FilterParams& fp, int32_t* d_cost, int32_t* d_sad,
-                         int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, bool lone_frame, cudaStream_t st) {
+                         int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, bool lone_frame, bool compact, cudaStream_t st) {
+    if (compact && (bit_depth > 10 || d_sad)) return cudaErrorInvalidValue;      // 16-bit entries hold 2 * 32 * 1023, not 2 * 32 * 4095
     if (bit_depth != 8 && bit_depth != 10 && bit_depth != 12) return cudaErrorInvalidValue;
     if ((d_best_mode == nullptr) != (d_best_cost == nullptr) || (d_sad == nullptr) != (d_satd == nullptr)) return cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(d_frame) & 15) != 0) return cudaErrorMisalignedAddress;   // TMA needs a 16-byte aligned frame
@@ -1130,7 +1146,7 @@ cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, int bit_depth, c
     if (e != cudaSuccess) return e;
     const int nctu = ((W + 127) >> 7) * ((H + 127) >> 7);
     const int split = lone_frame ? 1 : 0;
-    mip_cost_kernel<<<nctu * 2 * g_chunks[split], NT, SM_TOTAL, st>>>(map, fp, W, H, split, (1 << bit_depth) - 1, d_cost, d_sad, d_satd, d_best_mode, d_best_cost);
+    mip_cost_kernel<<<nctu * 2 * g_chunks[split], NT, SM_TOTAL, st>>>(map, fp, W, H, split, (1 << bit_depth) - 1, compact ? 1 : 0, d_cost, d_sad, d_satd, d_best_mode, d_best_cost);
     return cudaGetLastError();
 }
 

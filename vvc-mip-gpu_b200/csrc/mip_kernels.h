@@ -33,7 +33,8 @@ cudaError_t make_filter_params(int filter_type, int kernel_idx, int bit_depth, F
 // bit_depth: 10 = the reference (clamp 1023, default sample 512: intra.cl:61, 446, 482); 8 and 12 scale those constants.
 // lone_frame: nothing else will share the GPU with this launch -> the split with the short tail (see kernels_init).
 cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, int bit_depth, const FilterParams& fp, int32_t* d_cost,
-                         int32_t* d_sad, int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, bool lone_frame, cudaStream_t st);
+                         int32_t* d_sad, int32_t* d_satd, uint8_t* d_best_mode, int32_t* d_best_cost, bool lone_frame, bool compact,
+                         cudaStream_t st);   // compact: d_cost is a compact table (mip_compact.h), bit depth <= 10, no SAD / SATD
 
 // Low-pass filter of a whole frame (alternative samples), filter_type 1..8.
 cudaError_t launch_filter(const uint16_t* d_in, uint16_t* d_out, int W, int H, int filter_type, int kernel_idx,

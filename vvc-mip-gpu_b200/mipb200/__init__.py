@@ -27,6 +27,8 @@ SKIPPED = -1
 EMIT_COSTS = 1
 EMIT_SAD_SATD = 2
 EMIT_DECISIONS = 4
+EMIT_COSTS_COMPACT = 8
+COMPACT_BYTES_PER_CTU = 276672
 TOPK_MAX = 12
 LAUNCH_AUTO, LAUNCH_THROUGHPUT, LAUNCH_LATENCY = 0, 1, 2
 
@@ -34,7 +36,7 @@ LAUNCH_AUTO, LAUNCH_THROUGHPUT, LAUNCH_LATENCY = 0, 1, 2
 ABI_SYMBOLS = (
     "mipb200_create", "mipb200_destroy", "mipb200_next_input", "mipb200_submit", "mipb200_collect",
     "mipb200_in_flight", "mipb200_set_launch_mode", "mipb200_num_ctus", "mipb200_device_count", "mipb200_run_device", "mipb200_filter_device",
-    "mipb200_decide_device", "mipb200_topk_device", "mipb200_kernel_launches", "mipb200_device_energy_mj", "mipb200_pin_host", "mipb200_pin_host_on", "mipb200_unpin_host", "mipb200_sync", "mipb200_last_error",
+    "mipb200_decide_device", "mipb200_topk_device", "mipb200_compact_bytes_per_ctu", "mipb200_expand_costs", "mipb200_kernel_launches", "mipb200_device_energy_mj", "mipb200_pin_host", "mipb200_pin_host_on", "mipb200_unpin_host", "mipb200_sync", "mipb200_last_error",
     "mipb200_version",
 )
 
@@ -60,6 +62,7 @@ class Result(ctypes.Structure):
         ("satd", ctypes.POINTER(ctypes.c_int32)), ("best_mode", ctypes.POINTER(ctypes.c_uint8)),
         ("best_cost", ctypes.POINTER(ctypes.c_int32)), ("gpu_ms", ctypes.c_float),
         ("top_k", ctypes.c_int), ("topk_mode", ctypes.POINTER(ctypes.c_uint8)), ("topk_cost", ctypes.POINTER(ctypes.c_int32)),
+        ("cost_compact", ctypes.POINTER(ctypes.c_uint8)),
     ]
 
 
@@ -109,6 +112,10 @@ def lib() -> ctypes.CDLL:
         L.mipb200_decide_device.restype = ctypes.c_int
         L.mipb200_topk_device.argtypes = [vp, vp, ctypes.c_int, vp, vp, vp]
         L.mipb200_topk_device.restype = ctypes.c_int
+        L.mipb200_compact_bytes_per_ctu.argtypes = []
+        L.mipb200_compact_bytes_per_ctu.restype = ctypes.c_size_t
+        L.mipb200_expand_costs.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int]
+        L.mipb200_expand_costs.restype = ctypes.c_int
         L.mipb200_kernel_launches.argtypes = [vp]
         L.mipb200_kernel_launches.restype = ctypes.c_longlong
         L.mipb200_device_energy_mj.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
@@ -172,6 +179,19 @@ class FrameResult:
         self.top_k = int(r.top_k)
         self.topk_mode = view(r.topk_mode, (n, CUS_PER_CTU, self.top_k), np.uint8) if self.top_k else None
         self.topk_cost = view(r.topk_cost, (n, CUS_PER_CTU, self.top_k), np.int32) if self.top_k else None
+        self.cost_compact = view(r.cost_compact, (n, COMPACT_BYTES_PER_CTU), np.uint8)
+
+    def expand_costs(self, threads: int = 1) -> np.ndarray:
+        """The compact table (EMIT_COSTS_COMPACT) as the int32 table [n_ctus][97840]."""
+        return expand_costs(self.cost_compact, threads)
+
+
+def expand_costs(compact: np.ndarray, threads: int = 1) -> np.ndarray:
+    """mipb200_expand_costs(): uint8 [n_ctus][COMPACT_BYTES_PER_CTU] -> int32 [n_ctus][97840]."""
+    compact = np.ascontiguousarray(compact, dtype=np.uint8).reshape(-1, COMPACT_BYTES_PER_CTU)
+    out = np.empty((compact.shape[0], COSTS_PER_CTU), dtype=np.int32)
+    _check(lib().mipb200_expand_costs(compact.ctypes.data, compact.shape[0], out.ctypes.data, threads))
+    return out
 
 
 class Engine:

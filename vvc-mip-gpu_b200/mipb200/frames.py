@@ -128,3 +128,19 @@ def read_decisions_dump(path: str):
     modes = rec[:, :n].reshape(shape)
     costs = np.ascontiguousarray(rec[:, n:]).view("<i4").reshape(shape)
     return hdr, modes, costs
+
+
+def read_compact_dump(path: str):
+    """Reads a `mipb200_main --CompactLog` file -> (header dict, uint8 records [frames][nCTU][276672]).
+    Layout: 64-byte header = "MIPB200K", then little-endian u32 version, width, height, frames, CTUs, bytes per CTU, bit
+    depth, filter type, kernel index; then one compact record per CTU and frame in POC order (csrc/mip_compact.h: uint16
+    entries for CU types of at most 32 samples, int32 for the others; mipb200.expand_costs() gives the int32 table)."""
+    with open(path, "rb") as f:
+        raw = f.read(64)
+        if len(raw) != 64 or raw[:8] != b"MIPB200K":
+            raise ValueError(f"{path} is not a mipb200 compact cost dump")
+        v = np.frombuffer(raw[8:48], dtype="<u4")
+        hdr = dict(version=int(v[0]), width=int(v[1]), height=int(v[2]), frames=int(v[3]), n_ctus=int(v[4]), bytes_per_ctu=int(v[5]),
+                   bit_depth=int(v[6]), filter_type=int(v[7]), kernel_idx=int(v[8]))
+        data = np.fromfile(f, dtype=np.uint8)
+    return hdr, data.reshape(hdr["frames"], hdr["n_ctus"], hdr["bytes_per_ctu"])
