@@ -1061,8 +1061,6 @@ cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
     return cudaSuccess;
 }
 
-int kernels_chunks_per_ctu() { return g_chunks[0]; }
-
 // cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no -lcuda at link time)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -10,7 +10,6 @@ namespace mipb200 {
 // nchunks[sp] = chunks per half, weights[sp] (may be null: equal) = relative cost share of each chunk, in launch order.
 // cudaErrorInvalidValue: a chunk would hold more CUs than the shared-memory decision table (use more chunks).
 cudaError_t kernels_init(const int* nchunks, const double* const* weights);
-int kernels_chunks_per_ctu();
 
 // Low-pass filter of the fused path, prepared once per engine and passed to the kernel by value (constant-bank
 // operands): the (2R+1)^2 tap weights (k (x) k for the 1-D types), the denominator of a sample whose whole window
