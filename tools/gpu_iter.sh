@@ -1,8 +1,8 @@
 #!/bin/bash
-# Quick iteration on the GPU box: parity tests, then kernel timing of the hot path.
+# kernel iteration: parity subset + steady-state / lone-frame timing for a list of throughput splits
 set -u
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -5
-python tools/profile_run.py 20 2>&1 | tail -2
-python tools/profile_run.py 20 3840x2160 2>&1 | tail -1
-if [ "${1:-}" = "mb" ]; then tools/bin/microbench gpurun_out/microbench.json | tail -14; fi
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py tests/test_gpu_engine.py -m gpu -x -q 2>&1 | tail -4
+rm -f gpurun_out/iter_timing.jsonl
+for w in ${SPLITS:-"1,1,1" "1,1" "1" "3,2" "1,1,1,1"}; do MODE=throughput MIPB200_CHUNK_WEIGHTS=$w timeout 300 python tools/chunk_sweep.py 1920x1080 96 | tee -a gpurun_out/iter_timing.jsonl; done
+MODE=latency timeout 300 python tools/chunk_sweep.py 1920x1080 96 | tee -a gpurun_out/iter_timing.jsonl
