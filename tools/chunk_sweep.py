@@ -21,7 +21,7 @@ emit = mipb200.EMIT_COSTS | mipb200.EMIT_DECISIONS
 pool = torch.from_numpy(np.stack([frames.natural_frame(W, H, i) for i in range(4)]).view(np.int16)).cuda()
 mode = {"auto": mipb200.LAUNCH_AUTO, "throughput": mipb200.LAUNCH_THROUGHPUT, "latency": mipb200.LAUNCH_LATENCY}[os.environ.get("MODE", "auto")]
 res = {"weights": os.environ.get("MIPB200_CHUNK_WEIGHTS"), "weights_lone": os.environ.get("MIPB200_CHUNK_WEIGHTS_LONE"), "mode": os.environ.get("MODE", "auto"), "size": f"{W}x{H}"}
-for ns in (1, 3):
+for ns in tuple(int(v) for v in os.environ.get('STREAMS', '1,3').split(',')):
     engs = [mipb200.Engine(W, H, filter_type=8, kernel_idx=2, slots=1, emit=emit) for _ in range(ns)]
     n = engs[0].n_ctus
     for e_ in engs:
@@ -50,7 +50,7 @@ for ns in (1, 3):
         e1.record(streams[0])
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / N)
-    res["ms_1stream" if ns == 1 else "ms_3streams"] = round(best, 4)
+    res["ms_1stream" if ns == 1 else f"ms_{ns}streams"] = round(best, 4)
     res["checksum"] = int(outs[0][0].to(torch.int64).clamp(min=0).sum()) ^ int(outs[0][2].to(torch.int64).sum())
     for e in engs:
         e.close()

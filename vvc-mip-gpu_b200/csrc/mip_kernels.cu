@@ -617,8 +617,11 @@ __device__ __forceinline__ void build_ref_tile(uint16_t* s_refT, uint16_t* s_ref
 // ------------------------------------------------------------------------------------------
 // The fused kernel
 // ------------------------------------------------------------------------------------------
+// COMPACT: the cost table is the compact one (mip_compact.h).  A template parameter, not an argument: the int32 path pays
+// nothing for the other's existence (as an argument it cost 0.6 % of the frame).
+template <bool COMPACT>
 __global__ void __launch_bounds__(NT, 2)
-mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams fp, int W, int H, int split, int maxv, int compact,
+mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams fp, int W, int H, int split, int maxv,
                 int32_t* __restrict__ g_cost, int32_t* __restrict__ g_sad, int32_t* __restrict__ g_satd,
                 uint8_t* __restrict__ g_best_mode, int32_t* __restrict__ g_best_cost) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -755,7 +758,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             const uint32_t o = ctuBase + coff;
             const int cost = min(2 * sad, satd);            // intra.cl:1166
             if (g_cost) {
-                if (!compact) g_cost[o] = active ? cost : -1;
+                if constexpr (!COMPACT) g_cost[o] = active ? cost : -1;
                 else {
                     // compact table (mip_compact.h): the type's block inside the CTU's record, 16-bit entries for CUs of at
                     // most 32 samples (cost <= 65 472 with 10-bit samples), int32 otherwise
@@ -1051,10 +1054,12 @@ cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
         if ((4095 * worst + 32) / 64 + 4096 >= 32768) return cudaErrorInvalidValue;
     }
     if ((err = cudaMemcpyToSymbol(g_mat, mat.data(), MAT_BYTES)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(mip_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(mip_cost_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(mip_cost_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(mip_cost_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(mip_cost_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(mip_cost_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return err;
     int ctas = 0;
-    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, mip_cost_kernel, NT, SM_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, mip_cost_kernel<false>, NT, SM_TOTAL)) != cudaSuccess) return err;
     if (getenv("MIPB200_VERBOSE")) fprintf(stderr, "mipb200: cost kernel %d threads, %d B smem, %d CTA(s)/SM, %d / %d chunks per CTU half (throughput / lone frame)\n", NT, SM_TOTAL, ctas, chunks_of[0], chunks_of[1]);
     g_chunks[0] = chunks_of[0];
     g_chunks[1] = chunks_of[1];
@@ -1144,7 +1149,9 @@ cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, int bit_depth, c
     if (e != cudaSuccess) return e;
     const int nctu = ((W + 127) >> 7) * ((H + 127) >> 7);
     const int split = lone_frame ? 1 : 0;
-    mip_cost_kernel<<<nctu * 2 * g_chunks[split], NT, SM_TOTAL, st>>>(map, fp, W, H, split, (1 << bit_depth) - 1, compact ? 1 : 0, d_cost, d_sad, d_satd, d_best_mode, d_best_cost);
+    const int grid = nctu * 2 * g_chunks[split], maxv = (1 << bit_depth) - 1;
+    if (compact) mip_cost_kernel<true><<<grid, NT, SM_TOTAL, st>>>(map, fp, W, H, split, maxv, d_cost, d_sad, d_satd, d_best_mode, d_best_cost);
+    else mip_cost_kernel<false><<<grid, NT, SM_TOTAL, st>>>(map, fp, W, H, split, maxv, d_cost, d_sad, d_satd, d_best_mode, d_best_cost);
     return cudaGetLastError();
 }
 
