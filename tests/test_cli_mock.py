@@ -226,3 +226,14 @@ def test_compact_log(mock_cli, oracle, tmp_path, mip):
     assert open(dig).read().splitlines()[0] == "POC,CostsCompact,Modes,BestCosts"
     r = mock_cli("-f", "1", "-s", f"{W}x{H}", "-o", str(raw), "--InputFormat=u16", f"--CompactLog={dump}")
     assert r.returncode == 1 and "CompactLog needs --NoLog" in r.stdout
+
+
+def test_slots_and_ring_arguments(mock_cli, tmp_path):
+    raw = tmp_path / "in.u16"
+    np.zeros((2, 128, 128), dtype="<u2").tofile(str(raw))
+    r = mock_cli("-f", "2", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", "--Slots=0")
+    assert r.returncode == 1 and "Slots must be in 1..16" in r.stdout
+    r = mock_cli("-f", "2", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", "--Slots=5", "--InputFrames=1")
+    assert r.returncode == 0 and "Frame ring: 1 x" in r.stdout and "resident" in r.stdout and "Peak host memory (MB)," in r.stdout
+    r = mock_cli("-f", "2", "-s", "128x128", "-o", str(raw), "--InputFormat=u16", "--NoLog", "--RingFrames=-1")
+    assert r.returncode == 1 and "must be positive" in r.stdout

@@ -226,3 +226,22 @@ def test_compact_cost_table(mip, oracle, ft, kidx):
         with pytest.raises(mip.MipError) as ei:
             mip.Engine(W, H, **kw)
         assert ei.value.code == -1
+
+
+def test_device_timeline_trace(mip, tmp_path, monkeypatch):
+    """MIPB200_TRACE=<file>: one line per collected frame, upload start <= kernel start <= kernel end <= results on the host."""
+    from mipb200 import frames
+    monkeypatch.setenv("MIPB200_TRACE", str(tmp_path / "trace"))
+    f = frames.noise_frame(256, 128, 5)
+    with mip.Engine(256, 128, slots=2, emit=mip.EMIT_DECISIONS) as eng:
+        for i in range(4):
+            eng.submit(f, i)
+            if eng.in_flight() == 2:
+                eng.collect()
+        while eng.in_flight():
+            eng.collect()
+    lines = [ln for ln in open(str(tmp_path / "trace") + ".gpu0").read().splitlines() if not ln.startswith("#")]
+    assert [int(ln.split()[0]) for ln in lines] == [0, 1, 2, 3]
+    for ln in lines:
+        t = [float(v) for v in ln.split()[1:]]
+        assert t == sorted(t) and t[3] - t[0] < 1000.0

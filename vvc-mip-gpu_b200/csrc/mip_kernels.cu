@@ -619,7 +619,9 @@ __device__ __forceinline__ void build_ref_tile(uint16_t* s_refT, uint16_t* s_ref
 // ------------------------------------------------------------------------------------------
 // COMPACT: the cost table is the compact one (mip_compact.h).  A template parameter, not an argument: the int32 path pays
 // nothing for the other's existence (as an argument it cost 0.6 % of the frame).
-template <bool COMPACT>
+// OUT: which results the launch writes -- template parameters, not pointer tests per warp task (a frame is 390 000 tasks).
+constexpr int OUT_COST = 1, OUT_SADSATD = 2, OUT_DEC = 4;
+template <bool COMPACT, int OUT>
 __global__ void __launch_bounds__(NT, 2)
 mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams fp, int W, int H, int split, int maxv,
                 int32_t* __restrict__ g_cost, int32_t* __restrict__ g_sad, int32_t* __restrict__ g_satd,
@@ -683,7 +685,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         }
     }
     const int ordBeg = c_chunk_ord[split][half][chunk], ordCnt = c_chunk_ord[split][half][chunk + 1] - ordBeg;
-    if (g_best_mode)
+    if constexpr (OUT & OUT_DEC)
         for (int i = tid; i < ordCnt; i += NT) s_dec[i] = 0xffffffffu;
     if (tid == 0) { *s_dc = (uint16_t)((maxv + 1) >> 1); *s_next = 0; }
     __syncthreads();                                      // tiles complete; the staging box may now be overwritten
@@ -757,7 +759,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         if (inRange && part == 0) {
             const uint32_t o = ctuBase + coff;
             const int cost = min(2 * sad, satd);            // intra.cl:1166
-            if (g_cost) {
+            if constexpr (OUT & OUT_COST) {
                 if constexpr (!COMPACT) g_cost[o] = active ? cost : -1;
                 else {
                     // compact table (mip_compact.h): the type's block inside the CTU's record, 16-bit entries for CUs of at
@@ -768,9 +770,9 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     else reinterpret_cast<int32_t*>(rec)[idx] = active ? cost : -1;
                 }
             }
-            if (g_sad) { g_sad[o] = active ? sad : -1; g_satd[o] = active ? satd : -1; }   // both or neither (launch_costs)
+            if constexpr (OUT & OUT_SADSATD) { g_sad[o] = active ? sad : -1; g_satd[o] = active ? satd : -1; }   // both or neither (launch_costs)
         }
-        if (g_best_mode) {
+        if constexpr (OUT & OUT_DEC) {
             // decision = argmin over the CU's modes, lowest mode wins ties: min of (cost << 6 | mode), cost < 2^24.
             // The lanes of one CU are first reduced in registers (MATCH.ANY + REDUX.MIN), then one lane per CU does the
             // shared-memory atomicMin: 3-4 distinct addresses per warp instead of 32 lanes serialising on them.
@@ -795,7 +797,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         }
         lr = lr_next;
     }
-    if (g_best_mode) {
+    if constexpr (OUT & OUT_DEC) {
         __syncthreads();
         const size_t cuBase = (size_t)ctu * MIP_CUS_PER_CTU;
         for (int i = tid; i < ordCnt; i += NT) {
@@ -925,6 +927,23 @@ mip_topk_kernel(const int32_t* __restrict__ cost, int n_ctus, int k, uint8_t* __
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
+// the instantiations that exist: variant = OUT | COMPACT << 3 (the compact table excludes SAD / SATD)
+constexpr int NUM_VARIANTS = 16;
+static const void* cost_kernel_variant(int v) {
+    switch (v) {
+        case OUT_DEC: return (const void*)mip_cost_kernel<false, OUT_DEC>;
+        case OUT_COST: return (const void*)mip_cost_kernel<false, OUT_COST>;
+        case OUT_COST | OUT_DEC: return (const void*)mip_cost_kernel<false, OUT_COST | OUT_DEC>;
+        case OUT_COST | OUT_SADSATD: return (const void*)mip_cost_kernel<false, OUT_COST | OUT_SADSATD>;
+        case OUT_COST | OUT_SADSATD | OUT_DEC: return (const void*)mip_cost_kernel<false, OUT_COST | OUT_SADSATD | OUT_DEC>;
+        case OUT_SADSATD: return (const void*)mip_cost_kernel<false, OUT_SADSATD>;
+        case OUT_SADSATD | OUT_DEC: return (const void*)mip_cost_kernel<false, OUT_SADSATD | OUT_DEC>;
+        case 8 | OUT_COST: return (const void*)mip_cost_kernel<true, OUT_COST>;
+        case 8 | OUT_COST | OUT_DEC: return (const void*)mip_cost_kernel<true, OUT_COST | OUT_DEC>;
+        default: return nullptr;
+    }
+}
+
 cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
     // cum[sp][k] = share of a half's cost that lies before chunk k of split sp (equal shares unless weights are given)
     double cum[2][MAX_CHUNKS + 1];
@@ -1054,12 +1073,14 @@ cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
         if ((4095 * worst + 32) / 64 + 4096 >= 32768) return cudaErrorInvalidValue;
     }
     if ((err = cudaMemcpyToSymbol(g_mat, mat.data(), MAT_BYTES)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(mip_cost_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(mip_cost_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(mip_cost_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(mip_cost_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return err;
     int ctas = 0;
-    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, mip_cost_kernel<false>, NT, SM_TOTAL)) != cudaSuccess) return err;
+    for (int v = 0; v < NUM_VARIANTS; ++v) {
+        const void* fn = cost_kernel_variant(v);
+        if (!fn) continue;
+        if ((err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)) != cudaSuccess) return err;
+        if ((err = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return err;
+        if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, fn, NT, SM_TOTAL)) != cudaSuccess) return err;
+    }
     if (getenv("MIPB200_VERBOSE")) fprintf(stderr, "mipb200: cost kernel %d threads, %d B smem, %d CTA(s)/SM, %d / %d chunks per CTU half (throughput / lone frame)\n", NT, SM_TOTAL, ctas, chunks_of[0], chunks_of[1]);
     g_chunks[0] = chunks_of[0];
     g_chunks[1] = chunks_of[1];
@@ -1149,9 +1170,13 @@ cudaError_t launch_costs(const uint16_t* d_frame, int W, int H, int bit_depth, c
     if (e != cudaSuccess) return e;
     const int nctu = ((W + 127) >> 7) * ((H + 127) >> 7);
     const int split = lone_frame ? 1 : 0;
-    const int grid = nctu * 2 * g_chunks[split], maxv = (1 << bit_depth) - 1;
-    if (compact) mip_cost_kernel<true><<<grid, NT, SM_TOTAL, st>>>(map, fp, W, H, split, maxv, d_cost, d_sad, d_satd, d_best_mode, d_best_cost);
-    else mip_cost_kernel<false><<<grid, NT, SM_TOTAL, st>>>(map, fp, W, H, split, maxv, d_cost, d_sad, d_satd, d_best_mode, d_best_cost);
+    const int grid = nctu * 2 * g_chunks[split];
+    int maxv = (1 << bit_depth) - 1;
+    const int variant = (d_cost ? OUT_COST : 0) | (d_sad ? OUT_SADSATD : 0) | (d_best_mode ? OUT_DEC : 0) | (compact ? 8 : 0);
+    const void* fn = cost_kernel_variant(variant);
+    if (!fn) return cudaErrorInvalidValue;           // no output at all, or SAD / SATD beside the compact table
+    void* args[] = {&map, const_cast<FilterParams*>(&fp), &W, &H, const_cast<int*>(&split), &maxv, &d_cost, &d_sad, &d_satd, &d_best_mode, &d_best_cost};
+    if ((e = cudaLaunchKernel(fn, dim3(grid), dim3(NT), args, SM_TOTAL, st)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
