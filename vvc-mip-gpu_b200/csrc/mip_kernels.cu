@@ -475,6 +475,21 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
     }
 }
 
+// One warp task of a known shape: the in-frame test with the CU size as immediates, the work, and -- for the 64x64 type,
+// whose (CU, mode) pairs take four lanes -- the sum over the four strip groups.  Returns whether this lane's CU is inside the frame.
+template <int SID, int W, int H, int PARTS = 1>
+__device__ __forceinline__ bool do_task(const Ctx& c, int cuX, int cuY, int mode, int part, bool inRange, int rowsValid, int frameW, int& sad, int& satd) {
+    const bool active = inRange && cuY + H <= rowsValid && c.ctuX + cuX + W <= frameW;   // CU fully inside the frame
+    if (__any_sync(0xffffffffu, active)) {
+        run_task<SID, W, H, PARTS>(c, cuX, cuY, mode, part, sad, satd);
+        if constexpr (PARTS == 4) {   // lanes 4k..4k+3 hold the four strip groups of one (CU, mode)
+            sad += __shfl_xor_sync(0xffffffffu, sad, 1);  satd += __shfl_xor_sync(0xffffffffu, satd, 1);
+            sad += __shfl_xor_sync(0xffffffffu, sad, 2);  satd += __shfl_xor_sync(0xffffffffu, satd, 2);
+        }
+    }
+    return active;
+}
+
 // ------------------------------------------------------------------------------------------
 // TMA + mbarrier (sm_90+/sm_100a PTX)
 // ------------------------------------------------------------------------------------------
@@ -705,7 +720,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     // Warp tasks are drawn from a shared-memory counter, one ahead: the record of the next task (one coalesced 8-byte load
     // from a table built once on the host -- the same 870 KB for every CTU, so it lives in L2) is requested before the
     // current task's arithmetic starts, which hides the atomic + L2 latency of the draw behind ~1000 instructions of work.
-    // Record: .x = cuX | cuY << 7 | mode << 13 | strip group << 18 | inRange << 20 | CU type << 21, .y = cost index in
+    // Record: .x = cuX | cuY << 7 | mode << 13 | strip group << 18 | inRange << 20 | shape << 21 | mode class << 26, .y = cost index in
     // the CTU | decision slot << 17.  0xffffffff in .x = no more work.
     auto draw = [&](uint32_t zero) -> uint2 {
         // Lane 0 draws.  ptxas wraps an atomic on a warp-uniform address into a vote / popc / shuffle aggregation (17
@@ -723,38 +738,32 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const uint2 lr_next = draw((lr.y >> 30) << 2);
         // warp task = 32 consecutive (CU, mode) pairs of one type: a warp touches at most 3-4 CUs, so the shared-memory
         // reads of originals and boundaries are mostly broadcasts (8 CUs x 4 modes per warp measured 60 % more bank conflicts)
-        const DevType& ty = c_types[(lr.x >> 21) & 63];
-        const int pl2 = ty.parts_log2;
+        // everything a task needs is in its record: no table look-up per task
         const int cuX = lr.x & 127, cuY = (lr.x >> 7) & 63, mode = (lr.x >> 13) & 31, part = (lr.x >> 18) & 3;
         const bool inRange = (lr.x >> 20) & 1;
+        const int mclass = (lr.x >> 26) & 3;          // 0: 12 modes, 1: 16, 2: 32
         const uint32_t coff = lr.y & 0x1ffffu;
         const int slot = (int)(lr.y >> 17);
-        const bool active = inRange && cuY + ty.h <= rowsValid && ctuX + cuX + ty.w <= W;   // CU fully inside the frame
         int sad = 0, satd = 0;
-        if (__any_sync(0xffffffffu, active)) {
-            switch (ty.shape) {
-                case S64x64: run_task<2, 64, 64, 4>(c, cuX, cuY, mode, part, sad, satd); break;
-                case S32x32: run_task<2, 32, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S32x16: run_task<2, 32, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S16x32: run_task<2, 16, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S32x8:  run_task<2, 32, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S8x32:  run_task<2, 8, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S16x16: run_task<2, 16, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S16x8:  run_task<2, 16, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S8x16:  run_task<2, 8, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S32x4:  run_task<1, 32, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S4x32:  run_task<1, 4, 32>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S16x4:  run_task<1, 16, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S4x16:  run_task<1, 4, 16>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S8x8:   run_task<1, 8, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S8x4:   run_task<1, 8, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
-                case S4x8:   run_task<1, 4, 8>(c, cuX, cuY, mode, 0, sad, satd); break;
-                default:     run_task<0, 4, 4>(c, cuX, cuY, mode, 0, sad, satd); break;
-            }
-            if (pl2) {   // lanes 4k..4k+3 hold the four strip groups of one (CU, mode)
-                sad += __shfl_xor_sync(0xffffffffu, sad, 1);  satd += __shfl_xor_sync(0xffffffffu, satd, 1);
-                sad += __shfl_xor_sync(0xffffffffu, sad, 2);  satd += __shfl_xor_sync(0xffffffffu, satd, 2);
-            }
+        bool active;
+        switch ((lr.x >> 21) & 31) {
+            case S64x64: active = do_task<2, 64, 64, 4>(c, cuX, cuY, mode, part, inRange, rowsValid, W, sad, satd); break;
+            case S32x32: active = do_task<2, 32, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S32x16: active = do_task<2, 32, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S16x32: active = do_task<2, 16, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S32x8:  active = do_task<2, 32, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S8x32:  active = do_task<2, 8, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S16x16: active = do_task<2, 16, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S16x8:  active = do_task<2, 16, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S8x16:  active = do_task<2, 8, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S32x4:  active = do_task<1, 32, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S4x32:  active = do_task<1, 4, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S16x4:  active = do_task<1, 16, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S4x16:  active = do_task<1, 4, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S8x8:   active = do_task<1, 8, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S8x4:   active = do_task<1, 8, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            case S4x8:   active = do_task<1, 4, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            default:     active = do_task<0, 4, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
         }
         if (inRange && part == 0) {
             const uint32_t o = ctuBase + coff;
@@ -764,6 +773,12 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 else {
                     // compact table (mip_compact.h): the type's block inside the CTU's record, 16-bit entries for CUs of at
                     // most 32 samples (cost <= 65 472 with 10-bit samples), int32 otherwise
+                    int lo = 0, hi = MIP_NUM_TYPES - 1;      // the type whose block holds this cost (last type with cost_off <= coff)
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (c_types[mid].cost_off <= coff) lo = mid; else hi = mid - 1;
+                    }
+                    const DevType& ty = c_types[lo];
                     unsigned char* rec = reinterpret_cast<unsigned char*>(g_cost) + (size_t)ctu * MIP_COMPACT_BYTES_PER_CTU + ty.cmp_off;
                     const uint32_t idx = coff - ty.cost_off;
                     if (ty.narrow) reinterpret_cast<uint16_t*>(rec)[idx] = active ? (uint16_t)cost : (uint16_t)0xFFFFu;
@@ -778,8 +793,8 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             // shared-memory atomicMin: 3-4 distinct addresses per warp instead of 32 lanes serialising on them.
             const bool vote = inRange && part == 0 && active;
             const uint32_t key = ((uint32_t)min(2 * sad, satd) << 6) | (uint32_t)mode;
-            const int modes = ty.modes;
-            if (modes >= 16) {
+            if (mclass) {
+                const int modes = mclass == 2 ? 32 : 16;
                 // 16 or 32 modes: a CU is exactly one half or one whole warp task (in range, active and voting as a whole),
                 // so its group is known without MATCH and its slot has a single writer: a plain store
                 const unsigned grp = modes == 32 ? 0xffffffffu : ((lane & 16) ? 0xffff0000u : 0x0000ffffu);
@@ -996,7 +1011,8 @@ cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
                     const int cx = s.xs[cu % s.cols], cy = s.ys[cu / s.cols] - hf * TILE_ROWS;
                     const uint32_t coff = s.cost_off + (uint32_t)cu * s.modes + mode, slot = (uint32_t)(ord_total[hf] + cu_local);
                     if (cx > 127 || cy < 0 || cy > 63 || mode > 31 || part > 3 || coff >= (1u << 17) || slot >= (1u << 12)) return cudaErrorInvalidValue;
-                    lanes[hf].push_back(make_uint2((uint32_t)cx | ((uint32_t)cy << 7) | ((uint32_t)mode << 13) | ((uint32_t)part << 18) | ((uint32_t)in_range << 20) | ((uint32_t)t << 21),
+                    lanes[hf].push_back(make_uint2((uint32_t)cx | ((uint32_t)cy << 7) | ((uint32_t)mode << 13) | ((uint32_t)part << 18) | ((uint32_t)in_range << 20) | ((uint32_t)d.shape << 21) |
+                                                   ((uint32_t)(s.modes == 12 ? 0 : s.modes == 16 ? 1 : 2) << 26) | ((uint32_t)d.parts_log2 << 28),
                                                    coff | (slot << 17)));
                 }
                 work[hf].push_back((uint32_t)t | ((uint32_t)w << 8));
