@@ -722,13 +722,18 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     // current task's arithmetic starts, which hides the atomic + L2 latency of the draw behind ~1000 instructions of work.
     // Record: .x = cuX | cuY << 7 | mode << 13 | strip group << 18 | inRange << 20 | shape << 21 | mode class << 26, .y = cost index in
     // the CTU | decision slot << 17.  0xffffffff in .x = no more work.
+    // shared-memory addresses used once per task, kept in registers (left to itself the compiler re-derives them from
+    // SR_CgaCtaId -- an S2R -- in every iteration)
+    uint32_t a_next, a_dec;
+    asm volatile("mov.u32 %0, %1;" : "=r"(a_next) : "r"(smem_u32(s_next)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(a_dec) : "r"(smem_u32(s_dec) - 4u * (uint32_t)ordBeg));
     auto draw = [&](uint32_t zero) -> uint2 {
         // Lane 0 draws.  ptxas wraps an atomic on a warp-uniform address into a vote / popc / shuffle aggregation (17
         // instructions); `zero` -- bits of a loaded record that are always 0, which the compiler cannot know -- makes the
         // address formally per-lane and leaves a single predicated ATOMS.ADD.
         int wi;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\tmov.s32 %0, 0;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
-                     : "=r"(wi) : "r"(lane), "r"(smem_u32(s_next) + zero) : "memory");
+                     : "=r"(wi) : "r"(lane), "r"(a_next + zero) : "memory");
         wi = __shfl_sync(0xffffffffu, wi, 0);
         if (wi >= wcnt) return make_uint2(0xffffffffu, 0u);
         return __ldg(&g_lane[half][wbeg + wi][lane]);
@@ -800,13 +805,13 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 const unsigned grp = modes == 32 ? 0xffffffffu : ((lane & 16) ? 0xffff0000u : 0x0000ffffu);
                 if (vote) {
                     const uint32_t best = __reduce_min_sync(grp, key);
-                    if ((lane & (modes - 1)) == 0) s_dec[slot - ordBeg] = best;
+                    if ((lane & (modes - 1)) == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_dec + 4u * (uint32_t)slot), "r"(best) : "memory");
                 }
             } else {
                 const unsigned grp = __match_any_sync(0xffffffffu, vote ? slot : -1 - lane);
                 if (vote) {
                     const uint32_t best = __reduce_min_sync(grp, key);
-                    if (lane == __ffs(grp) - 1) atomicMin(&s_dec[slot - ordBeg], best);
+                    if (lane == __ffs(grp) - 1) asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a_dec + 4u * (uint32_t)slot), "r"(best) : "memory");
                 }
             }
         }
