@@ -139,9 +139,11 @@ static int shape_of(int w, int h) {
 // ------------------------------------------------------------------------------------------
 struct Ctx {
     const int* s_orig;        // [128][OS], holds orig + 1
-    const uint16_t* s_refT;   // row slots:    sample (slot, x) at slot * RT_STRIDE + 8 + x
-    const uint16_t* s_refL;   // column slots: sample (slot, y) at slot * RL_STRIDE + 8 + y
-    const uint16_t* s_dc;     // one cell holding 1 << (bitDepth - 1)
+    // reference samples are addressed by 32-bit shared-memory addresses held in registers (as generic pointers the
+    // compiler re-derives the shared window base -- an S2R of SR_CgaCtaId -- three or four times per warp task)
+    uint32_t a_refT;          // row slots:    sample (slot, x) at 2 * (slot * RT_STRIDE + 8 + x)
+    uint32_t a_refL;          // column slots: sample (slot, y) at 2 * (slot * RL_STRIDE + 8 + y)
+    uint32_t a_dc;            // one cell holding 1 << (bitDepth - 1)
     int maxv;                 // (1 << bitDepth) - 1
     uint32_t maxv2;           // maxv in both 16-bit halves
     uint32_t* s_red;          // this thread's column of the [RED_WORDS][NT] scratch
@@ -265,16 +267,27 @@ __device__ __forceinline__ void hor_row(const char* pa, const char* pb, bool fir
 // Reduced boundary (intra.cl:127-141, 260-279): B rounded means over D consecutive 16-bit samples each, p 8-byte aligned
 // (CU positions are multiples of 4).  64-bit shared loads; IDP.2A against (1, 1) adds a pair of samples per instruction
 // and starts from the rounding offset D / 2.
+__device__ __forceinline__ int lds_u16(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return (int)v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+
 template <int B, int D>
-__device__ __forceinline__ void reduce_bdry(const uint16_t* p, int (&red)[B]) {
+__device__ __forceinline__ void reduce_bdry(uint32_t p, int (&red)[B]) {
     if constexpr (D == 1) {
-        const uint2 v = *reinterpret_cast<const uint2*>(p);
+        const uint2 v = lds_v2(p);
         red[0] = v.x & 0xffff; red[1] = v.x >> 16; red[2] = v.y & 0xffff; red[3] = v.y >> 16;
     } else {
         uint32_t w[B * D / 2];
 #pragma unroll
         for (int i = 0; i < B * D / 4; ++i) {
-            const uint2 v = reinterpret_cast<const uint2*>(p)[i];
+            const uint2 v = lds_v2(p + 8 * i);
             w[2 * i] = v.x; w[2 * i + 1] = v.y;
         }
 #pragma unroll
@@ -299,14 +312,14 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 
     // ---- A.1 complete boundaries: pointer + stride into the reference tile (intra.cl:96-107, 232-243)
     const int absX = c.ctuX + cuX, absY = c.tileY + cuY;
-    const uint16_t *T, *L;
-    int stT, stL;
-    if (absY > 0) { T = c.s_refT + (cuY >> 2) * RT_STRIDE + 8 + cuX; stT = 1; }          // row Y-1 = slot cuY/4
-    else if (absX == 0) { T = c.s_dc; stT = 0; }
-    else { T = c.s_refT + RT_ROW0 * RT_STRIDE + 8 + cuX - 1; stT = 0; }                   // F[0][X-1] replicated
-    if (absX > 0) { L = c.s_refL + (cuX >> 2) * RL_STRIDE + 8 + cuY; stL = 1; }          // column X-1 = slot cuX/4
-    else if (absY == 0) { L = c.s_dc; stL = 0; }
-    else { L = c.s_refL + RL_COL0 * RL_STRIDE + 8 + cuY - 1; stL = 0; }                   // F[Y-1][0] replicated
+    uint32_t T, L;      // shared-memory byte addresses of the boundaries' first samples
+    int stT, stL;       // byte stride between samples: 2, or 0 for a replicated sample
+    if (absY > 0) { T = c.a_refT + 2 * ((cuY >> 2) * RT_STRIDE + 8 + cuX); stT = 2; }          // row Y-1 = slot cuY/4
+    else if (absX == 0) { T = c.a_dc; stT = 0; }
+    else { T = c.a_refT + 2 * (RT_ROW0 * RT_STRIDE + 8 + cuX - 1); stT = 0; }                   // F[0][X-1] replicated
+    if (absX > 0) { L = c.a_refL + 2 * ((cuX >> 2) * RL_STRIDE + 8 + cuY); stL = 2; }          // column X-1 = slot cuX/4
+    else if (absY == 0) { L = c.a_dc; stL = 0; }
+    else { L = c.a_refL + 2 * (RL_COL0 * RL_STRIDE + 8 + cuY - 1); stL = 0; }                   // F[Y-1][0] replicated
 
     // ---- A.2 reduced boundaries (intra.cl:127-141, 260-279)
     constexpr int DT = W / B, DL = H / B;
@@ -315,13 +328,13 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
         int redT[B], redL[B];
         if (stT) reduce_bdry<B, DT>(T, redT);
         else {   // frame edge: one replicated sample v, and (D * v + D / 2) >> log2(D) == v
-            const int v = T[0];
+            const int v = lds_u16(T);
 #pragma unroll
             for (int q = 0; q < B; ++q) redT[q] = v;
         }
         if (stL) reduce_bdry<B, DL>(L, redL);
         else {
-            const int v = L[0];
+            const int v = lds_u16(L);
 #pragma unroll
             for (int q = 0; q < B; ++q) redL[q] = v;
         }
@@ -406,13 +419,13 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
             constexpr int ROWB = RED_ROWB<R>;
             int prev[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) prev[k] = T[(x0 + k) * stT];
+            for (int k = 0; k < 4; ++k) prev[k] = lds_u16(T + (x0 + k) * stT);
             if constexpr (UV >= 4) {
                 constexpr int SH = UV == 4 ? 2 : 3;
 #pragma unroll 1
                 for (int j = 0; j < R; ++j) {
                     int cur[4];
-                    hor_row<UH>(sp.a + j * ROWB, sp.b + j * ROWB, sp.first, sp.odd, (int)L[(j * UV + UV - 1) * stL], cur);
+                    hor_row<UH>(sp.a + j * ROWB, sp.b + j * ROWB, sp.first, sp.odd, lds_u16(L + (j * UV + UV - 1) * stL), cur);
                     // nv = ~(UV*prev + UV/2 + i*dl) + UV walks down the rows; see diff_shifted()
                     int dl[4], nv[4];
 #pragma unroll
@@ -439,8 +452,8 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 #pragma unroll 1
                 for (int jp = 0; jp < R / 2; ++jp) {
                     int c0[4], c1[4], d[16], o1[4];
-                    hor_row<UH>(sp.a + 2 * jp * ROWB, sp.b + 2 * jp * ROWB, sp.first, sp.odd, (int)L[(4 * jp + 1) * stL], c0);
-                    hor_row<UH>(sp.a + (2 * jp + 1) * ROWB, sp.b + (2 * jp + 1) * ROWB, sp.first, sp.odd, (int)L[(4 * jp + 3) * stL], c1);
+                    hor_row<UH>(sp.a + 2 * jp * ROWB, sp.b + 2 * jp * ROWB, sp.first, sp.odd, lds_u16(L + (4 * jp + 1) * stL), c0);
+                    hor_row<UH>(sp.a + (2 * jp + 1) * ROWB, sp.b + (2 * jp + 1) * ROWB, sp.first, sp.odd, lds_u16(L + (4 * jp + 3) * stL), c1);
                     const int* o = orig + (4 * jp) * OS + x0;
                     load_o1_row(o, o1);            // row 0: (prev + c0 + 1) >> 1
 #pragma unroll
@@ -463,7 +476,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         int cur[4], o1[4];
-                        hor_row<UH>(sp.a + (4 * jq + i) * ROWB, sp.b + (4 * jq + i) * ROWB, sp.first, sp.odd, (int)L[(4 * jq + i) * stL], cur);
+                        hor_row<UH>(sp.a + (4 * jq + i) * ROWB, sp.b + (4 * jq + i) * ROWB, sp.first, sp.odd, lds_u16(L + (4 * jq + i) * stL), cur);
                         load_o1_row(orig + (4 * jq + i) * OS + x0, o1);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) d[4 * i + k] = diff_plain(o1[k], cur[k]);
@@ -707,9 +720,9 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 
     Ctx c;
     c.s_orig = s_orig;
-    c.s_refT = s_refT;
-    c.s_refL = s_refL;
-    c.s_dc = s_dc;
+    asm volatile("mov.u32 %0, %1;" : "=r"(c.a_refT) : "r"(smem_u32(s_refT)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(c.a_refL) : "r"(smem_u32(s_refL)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(c.a_dc) : "r"(smem_u32(s_dc)));
     c.maxv = maxv;
     c.maxv2 = (uint32_t)maxv * 0x10001u;
     c.s_red = s_red + tid;
