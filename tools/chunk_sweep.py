@@ -18,11 +18,12 @@ from mipb200 import frames
 W, H = (int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "1920x1080").split("x"))
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 96
 emit = mipb200.EMIT_COSTS | mipb200.EMIT_DECISIONS
+FT = int(os.environ.get("FILTER", "8"))      # 8 = the bench configuration (2-D 5x5), 0 = original samples
 pool = torch.from_numpy(np.stack([frames.natural_frame(W, H, i) for i in range(4)]).view(np.int16)).cuda()
 mode = {"auto": mipb200.LAUNCH_AUTO, "throughput": mipb200.LAUNCH_THROUGHPUT, "latency": mipb200.LAUNCH_LATENCY}[os.environ.get("MODE", "auto")]
-res = {"weights": os.environ.get("MIPB200_CHUNK_WEIGHTS"), "weights_lone": os.environ.get("MIPB200_CHUNK_WEIGHTS_LONE"), "mode": os.environ.get("MODE", "auto"), "size": f"{W}x{H}"}
+res = {"weights": os.environ.get("MIPB200_CHUNK_WEIGHTS"), "weights_lone": os.environ.get("MIPB200_CHUNK_WEIGHTS_LONE"), "mode": os.environ.get("MODE", "auto"), "filter": FT, "size": f"{W}x{H}"}
 for ns in tuple(int(v) for v in os.environ.get('STREAMS', '1,3').split(',')):
-    engs = [mipb200.Engine(W, H, filter_type=8, kernel_idx=2, slots=1, emit=emit) for _ in range(ns)]
+    engs = [mipb200.Engine(W, H, filter_type=FT, kernel_idx=2 if FT >= 5 else 0, slots=1, emit=emit) for _ in range(ns)]
     n = engs[0].n_ctus
     for e_ in engs:
         e_.set_launch_mode(mode)

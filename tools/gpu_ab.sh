@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 rm -f gpurun_out/ab_timing.jsonl
 if [ -n "${PARITY:-}" ]; then MIPB200_LIB=$PWD/vvc-mip-gpu_b200/lib/var_$PARITY.so timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py tests/test_gpu_engine.py -m gpu -x -q 2>&1 | tail -3; fi
-for rep in 1 2; do
+for rep in ${REPS:-1 2}; do
 for v in ${VARIANTS:-base}; do
   n=${v%%:*}; w=""; [ "$v" != "$n" ] && w=${v#*:}
   echo -n "$v: " | tee -a gpurun_out/ab_timing.jsonl
