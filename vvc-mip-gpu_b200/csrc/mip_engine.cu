@@ -119,7 +119,7 @@ struct mipb200_engine {
 };
 
 MIPB200_API const char* mipb200_last_error(void) { return g_err; }
-MIPB200_API const char* mipb200_version(void) { return "mipb200 0.1 (sm_100a)"; }
+MIPB200_API const char* mipb200_version(void) { return "mipb200 0.2 (sm_100a)"; }
 MIPB200_API int mipb200_num_ctus(int w, int h) { return ((w + 127) / 128) * ((h + 127) / 128); }
 
 static cudaError_t device_count(int* n) {
