@@ -114,6 +114,16 @@ constexpr int DEC_MAX = 2048;                  // CUs per chunk the shared-memor
 __constant__ uint16_t c_chunk_ord[2][2][MAX_CHUNKS + 1];   // first CU ordinal of each chunk (per split and half)
 __constant__ uint16_t c_ord2cu[2][2700];       // CU ordinal inside a half -> CU index inside the CTU (0..5379)
 __device__ uint2 g_lane[2][MAX_WORK][32];      // per (half, warp task, lane): what the lane does, see the task loop of mip_cost_kernel
+// Lane record: .x = cuX (byte 0; bit 7 is never set) | cuY (byte 1) | mode (byte 2) | strip group << 24 | flags, .y = cost index
+// in the CTU | decision slot << 17 | index of the shape inside its dispatch group << 29.  0xffffffff in .x = no more work.
+// Fields sit on byte boundaries (one PRMT each), flags are tested in place, and the CU shape is a prefix code -- one flag
+// bit per group, the most frequent group first -- instead of a number to be looked up in a 17-way switch.
+constexpr uint32_t REC_INRANGE = 1u << 26;     // the lane holds a real (CU, mode)
+constexpr uint32_t REC_WRITER = 1u << 27;      // ... and is the one that writes its cost (strip group 0)
+constexpr uint32_t REC_G64 = 1u << 28;         // 64x64 (12 modes, four lanes per (CU, mode))
+constexpr uint32_t REC_GS1 = 1u << 29;         // 8x8, 16x4, 4x16, 32x4, 4x32 (16 modes)
+constexpr uint32_t REC_GA32 = 1u << 30;        // 8x4, 4x8 (16 modes)
+constexpr uint32_t REC_G4x4 = 1u << 31;        // 4x4 (32 modes)
 __device__ uint8_t g_mat[MAT_BYTES];           // (coef - 32) as signed bytes, padded layout above
 
 static int g_chunks[2] = {0, 0};
@@ -146,7 +156,7 @@ struct Ctx {
     uint32_t a_dc;            // one cell holding 1 << (bitDepth - 1)
     int maxv;                 // (1 << bitDepth) - 1
     uint32_t maxv2;           // maxv in both 16-bit halves
-    uint32_t* s_red;          // this thread's column of the [RED_WORDS][NT] scratch
+    uint32_t a_red;           // this thread's column of the [RED_WORDS][NT] scratch (shared-memory address)
     const uint8_t* s_mat;
     int ctuX, tileY;          // frame position of the tile origin
 };
@@ -216,20 +226,27 @@ __device__ __forceinline__ void load_o1_row(const int* o, int (&v)[4]) {
 // sits in row 0; a row is RED_ROWB<R> bytes further down.
 constexpr int RED_WB = NT * 4;                                     // bytes between consecutive words of a lane's column
 template <int R> constexpr int RED_ROWB = (R / 2) * RED_WB;        // bytes between reduced rows
-__device__ __forceinline__ int ld_u16(const char* p) { return *reinterpret_cast<const uint16_t*>(p); }
+// The scratch column is read and written through shared-memory addresses with one LDS.U16 per sample: given pointers the
+// compiler fuses the loads of two neighbouring samples into an LDS.32 plus two extractions -- three instructions where two
+// do, in a kernel bound by instruction issue.  Volatile: stores and loads of the column keep their program order.
+__device__ __forceinline__ int ld_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return (int)v;
+}
+__device__ __forceinline__ void st_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 
-struct StripPtr { const char *a, *b; bool first; int odd; };
+struct StripPtr { uint32_t a, b; bool first; int odd; };
 template <int UH>
-__device__ __forceinline__ StripPtr strip_ptr(const uint32_t* s_red, int s) {
-    const char* base = reinterpret_cast<const char*>(s_red);
+__device__ __forceinline__ StripPtr strip_ptr(uint32_t base, int s) {
     StripPtr p;
     if constexpr (UH == 1) { p.a = base + 2 * s * RED_WB; p.b = p.a; p.first = false; p.odd = 0; }          // c = 4s .. 4s+3
-    else if constexpr (UH == 2) { p.a = base + s * RED_WB; p.b = p.a - RED_WB + 2; p.first = s == 0; p.odd = 0; }   // c = 2s, 2s+1; before: 2s-1
+    else if constexpr (UH == 2) { p.a = base + s * RED_WB; p.first = s == 0; p.b = p.first ? p.a : p.a - RED_WB + 2; p.odd = 0; }   // c = 2s, 2s+1; before: 2s-1
     else {
         const int c = UH == 4 ? s : (s >> 1);                                                                   // one reduced column
         p.a = base + (c >> 1) * RED_WB + (c & 1) * 2;
-        p.b = (c & 1) ? p.a - 2 : p.a - RED_WB + 2;
         p.first = c == 0;
+        p.b = (c & 1) ? p.a - 2 : (p.first ? p.a : p.a - RED_WB + 2);   // the first strip takes refL instead: any valid address
         p.odd = s & 1;
     }
     return p;
@@ -244,21 +261,21 @@ __device__ __forceinline__ int avg_up(int a, int b) {   // (a + b + 1) >> 1 as I
 }
 
 template <int UH>
-__device__ __forceinline__ void hor_row(const char* pa, const char* pb, bool first, int odd, int Lval, int (&cur)[4]) {
+__device__ __forceinline__ void hor_row(uint32_t pa, uint32_t pb, bool first, int odd, int Lval, int (&cur)[4]) {
     if constexpr (UH == 1) {
         cur[0] = ld_u16(pa); cur[1] = ld_u16(pa + 2); cur[2] = ld_u16(pa + RED_WB); cur[3] = ld_u16(pa + RED_WB + 2);
     } else if constexpr (UH == 2) {
         const int a0 = ld_u16(pa), a1 = ld_u16(pa + 2);
-        const int bef = first ? Lval : ld_u16(pb);
+        const int ldb = ld_u16(pb), bef = first ? Lval : ldb;
         cur[0] = avg_up(bef, a0); cur[1] = a0; cur[2] = avg_up(a0, a1); cur[3] = a1;
     } else if constexpr (UH == 4) {
         const int a = ld_u16(pa);
-        const int bef = first ? Lval : ld_u16(pb);
+        const int ldb = ld_u16(pb), bef = first ? Lval : ldb;
         const int dl = a - bef, v = 4 * bef + 2;
         cur[0] = (v + dl) >> 2; cur[1] = (v + 2 * dl) >> 2; cur[2] = (v + 3 * dl) >> 2; cur[3] = a;
     } else {  // UH == 8: two strips per reduced column
         const int a = ld_u16(pa);
-        const int bef = first ? Lval : ld_u16(pb);
+        const int ldb = ld_u16(pb), bef = first ? Lval : ldb;
         const int dl = a - bef, v = 8 * bef + 4 + odd * 4 * dl;
         cur[0] = (v + dl) >> 3; cur[1] = (v + 2 * dl) >> 3; cur[2] = (v + 3 * dl) >> 3; cur[3] = (v + 4 * dl) >> 3;
     }
@@ -392,7 +409,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
         // ---- A.3 matrix-vector product -> private scratch column, two samples per word
         const uint8_t* mb = c.s_mat + (SID == 2 ? (tr ? M2T_OFF : M2_OFF) + mat * M2_STRIDE : (tr ? M1T_OFF : M1_OFF) + mat * M1_STRIDE);
         const char* mp = reinterpret_cast<const char*>(mb);     // matrix rows a*R + b (8 taps each), two per 16-byte load
-        char* wp = reinterpret_cast<char*>(c.s_red);            // words of this lane's scratch column, RED_WB bytes apart
+        uint32_t wp = c.a_red;                                  // words of this lane's scratch column, RED_WB bytes apart
 #pragma unroll 1
         for (int a = 0; a < R; ++a) {
 #pragma unroll
@@ -404,7 +421,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
                 acc = __dp2a_lo(ipk[2], cw.y, acc);  acd = __dp2a_lo(ipk[2], cw.w, acd);
                 acc = __dp2a_hi(ipk[3], cw.y, acc);  acd = __dp2a_hi(ipk[3], cw.w, acd);
                 // bytes 1..2 of each accumulator = (4 * acc) >> 8 as a signed 16-bit value; clamp both halves to 0..maxv at once
-                *reinterpret_cast<uint32_t*>(wp + (b >> 1) * RED_WB) = __vimin_s16x2_relu(__byte_perm(acc, acd, 0x6521), c.maxv2);
+                st_u32(wp + (b >> 1) * RED_WB, __vimin_s16x2_relu(__byte_perm(acc, acd, 0x6521), c.maxv2));
             }
             mp += R * 8;
             wp += RED_ROWB<R>;
@@ -415,7 +432,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
 #pragma unroll 1
         for (int s = part * STRIPS; s < (part + 1) * STRIPS; ++s) {
             const int x0 = 4 * s;
-            const StripPtr sp = strip_ptr<UH>(c.s_red, s);
+            const StripPtr sp = strip_ptr<UH>(c.a_red, s);
             constexpr int ROWB = RED_ROWB<R>;
             int prev[4];
 #pragma unroll
@@ -725,7 +742,7 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     asm volatile("mov.u32 %0, %1;" : "=r"(c.a_dc) : "r"(smem_u32(s_dc)));
     c.maxv = maxv;
     c.maxv2 = (uint32_t)maxv * 0x10001u;
-    c.s_red = s_red + tid;
+    asm volatile("mov.u32 %0, %1;" : "=r"(c.a_red) : "r"(smem_u32(s_red + tid)));
     c.s_mat = s_mat;
     c.ctuX = ctuX;
     c.tileY = tileY;
@@ -733,57 +750,64 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     // Warp tasks are drawn from a shared-memory counter, one ahead: the record of the next task (one coalesced 8-byte load
     // from a table built once on the host -- the same 870 KB for every CTU, so it lives in L2) is requested before the
     // current task's arithmetic starts, which hides the atomic + L2 latency of the draw behind ~1000 instructions of work.
-    // Record: .x = cuX | cuY << 7 | mode << 13 | strip group << 18 | inRange << 20 | shape << 21 | mode class << 26, .y = cost index in
-    // the CTU | decision slot << 17.  0xffffffff in .x = no more work.
-    // shared-memory addresses used once per task, kept in registers (left to itself the compiler re-derives them from
-    // SR_CgaCtaId -- an S2R -- in every iteration)
+    // Everything a task needs is in its record (layout: see g_lane): no table look-up per task.
+    // Shared-memory addresses used once per task are kept in registers (left to itself the compiler re-derives them from
+    // SR_CgaCtaId -- an S2R -- in every iteration).
+    // Lane 0 draws.  ptxas wraps an atomic on a warp-uniform address into a vote / popc / shuffle aggregation (17
+    // instructions); adding bits of a loaded record that are always 0 -- which the compiler cannot know -- makes the address
+    // formally per-lane and leaves a single predicated ATOMS.ADD.
+    const uint2 lr0 = __ldg(&g_lane[half][min(wbeg, MAX_WORK - 1)][lane]);
     uint32_t a_next, a_dec;
-    asm volatile("mov.u32 %0, %1;" : "=r"(a_next) : "r"(smem_u32(s_next)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(a_next) : "r"(smem_u32(s_next) + ((lr0.x >> 5) & 4u)));
     asm volatile("mov.u32 %0, %1;" : "=r"(a_dec) : "r"(smem_u32(s_dec) - 4u * (uint32_t)ordBeg));
-    auto draw = [&](uint32_t zero) -> uint2 {
-        // Lane 0 draws.  ptxas wraps an atomic on a warp-uniform address into a vote / popc / shuffle aggregation (17
-        // instructions); `zero` -- bits of a loaded record that are always 0, which the compiler cannot know -- makes the
-        // address formally per-lane and leaves a single predicated ATOMS.ADD.
+    auto draw = [&]() -> uint2 {
         int wi;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\tmov.s32 %0, 0;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
-                     : "=r"(wi) : "r"(lane), "r"(a_next + zero) : "memory");
+                     : "=r"(wi) : "r"(lane), "r"(a_next) : "memory");
         wi = __shfl_sync(0xffffffffu, wi, 0);
         if (wi >= wcnt) return make_uint2(0xffffffffu, 0u);
         return __ldg(&g_lane[half][wbeg + wi][lane]);
     };
-    uint2 lr = draw((__ldg(&g_lane[half][min(wbeg, MAX_WORK - 1)][lane]).y >> 30) << 2);
+    uint2 lr = draw();
     while (lr.x != 0xffffffffu) {
-        const uint2 lr_next = draw((lr.y >> 30) << 2);
+        const uint2 lr_next = draw();
         // warp task = 32 consecutive (CU, mode) pairs of one type: a warp touches at most 3-4 CUs, so the shared-memory
         // reads of originals and boundaries are mostly broadcasts (8 CUs x 4 modes per warp measured 60 % more bank conflicts)
-        // everything a task needs is in its record: no table look-up per task
-        const int cuX = lr.x & 127, cuY = (lr.x >> 7) & 63, mode = (lr.x >> 13) & 31, part = (lr.x >> 18) & 3;
-        const bool inRange = (lr.x >> 20) & 1;
-        const int mclass = (lr.x >> 26) & 3;          // 0: 12 modes, 1: 16, 2: 32
+        const uint32_t x = lr.x;
+        const int cuX = x & 0xff, cuY = __byte_perm(x, 0, 0x4441), mode = __byte_perm(x, 0, 0x4442);
+        const bool inRange = (x & REC_INRANGE) != 0;
         const uint32_t coff = lr.y & 0x1ffffu;
-        const int slot = (int)(lr.y >> 17);
+        const int slot = (int)((lr.y >> 17) & 0xfffu);
+        const uint32_t sub = lr.y >> 29;
         int sad = 0, satd = 0;
         bool active;
-        switch ((lr.x >> 21) & 31) {
-            case S64x64: active = do_task<2, 64, 64, 4>(c, cuX, cuY, mode, part, inRange, rowsValid, W, sad, satd); break;
-            case S32x32: active = do_task<2, 32, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S32x16: active = do_task<2, 32, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S16x32: active = do_task<2, 16, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S32x8:  active = do_task<2, 32, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S8x32:  active = do_task<2, 8, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S16x16: active = do_task<2, 16, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S16x8:  active = do_task<2, 16, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S8x16:  active = do_task<2, 8, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S32x4:  active = do_task<1, 32, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S4x32:  active = do_task<1, 4, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S16x4:  active = do_task<1, 16, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S4x16:  active = do_task<1, 4, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S8x8:   active = do_task<1, 8, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S8x4:   active = do_task<1, 8, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            case S4x8:   active = do_task<1, 4, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
-            default:     active = do_task<0, 4, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+        if ((int)x < 0) active = do_task<0, 4, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd);
+        else if (x & REC_GA32) {
+            if (sub == 0) active = do_task<1, 8, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd);
+            else active = do_task<1, 4, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd);
+        } else if (x & REC_GS1) {
+            switch (sub) {
+                case 0:  active = do_task<1, 8, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+                case 1:  active = do_task<1, 16, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+                case 2:  active = do_task<1, 4, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+                case 3:  active = do_task<1, 32, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+                default: active = do_task<1, 4, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            }
+        } else if (x & REC_G64) active = do_task<2, 64, 64, 4>(c, cuX, cuY, mode, (x >> 24) & 3, inRange, rowsValid, W, sad, satd);
+        else {
+            switch (sub) {
+                case 0:  active = do_task<2, 32, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+                case 1:  active = do_task<2, 32, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+                case 2:  active = do_task<2, 16, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+                case 3:  active = do_task<2, 32, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+                case 4:  active = do_task<2, 8, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+                case 5:  active = do_task<2, 16, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+                case 6:  active = do_task<2, 16, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+                default: active = do_task<2, 8, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
+            }
         }
-        if (inRange && part == 0) {
+        const bool writer = (x & REC_WRITER) != 0;
+        if (writer) {
             const uint32_t o = ctuBase + coff;
             const int cost = min(2 * sad, satd);            // intra.cl:1166
             if constexpr (OUT & OUT_COST) {
@@ -809,12 +833,13 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             // decision = argmin over the CU's modes, lowest mode wins ties: min of (cost << 6 | mode), cost < 2^24.
             // The lanes of one CU are first reduced in registers (MATCH.ANY + REDUX.MIN), then one lane per CU does the
             // shared-memory atomicMin: 3-4 distinct addresses per warp instead of 32 lanes serialising on them.
-            const bool vote = inRange && part == 0 && active;
+            const bool vote = writer && active;
             const uint32_t key = ((uint32_t)min(2 * sad, satd) << 6) | (uint32_t)mode;
-            if (mclass) {
-                const int modes = mclass == 2 ? 32 : 16;
-                // 16 or 32 modes: a CU is exactly one half or one whole warp task (in range, active and voting as a whole),
-                // so its group is known without MATCH and its slot has a single writer: a plain store
+            if (x >= REC_GS1) {
+                // 16 or 32 modes (any of the three upper group flags): a CU is exactly one half or one whole warp task (in
+                // range, active and voting as a whole), so its group is known without MATCH and its slot has a single
+                // writer: a plain store
+                const int modes = (int)x < 0 ? 32 : 16;
                 const unsigned grp = modes == 32 ? 0xffffffffu : ((lane & 16) ? 0xffff0000u : 0x0000ffffu);
                 if (vote) {
                     const uint32_t best = __reduce_min_sync(grp, key);
@@ -1029,9 +1054,24 @@ cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
                     const int cx = s.xs[cu % s.cols], cy = s.ys[cu / s.cols] - hf * TILE_ROWS;
                     const uint32_t coff = s.cost_off + (uint32_t)cu * s.modes + mode, slot = (uint32_t)(ord_total[hf] + cu_local);
                     if (cx > 127 || cy < 0 || cy > 63 || mode > 31 || part > 3 || coff >= (1u << 17) || slot >= (1u << 12)) return cudaErrorInvalidValue;
-                    lanes[hf].push_back(make_uint2((uint32_t)cx | ((uint32_t)cy << 7) | ((uint32_t)mode << 13) | ((uint32_t)part << 18) | ((uint32_t)in_range << 20) | ((uint32_t)d.shape << 21) |
-                                                   ((uint32_t)(s.modes == 12 ? 0 : s.modes == 16 ? 1 : 2) << 26) | ((uint32_t)d.parts_log2 << 28),
-                                                   coff | (slot << 17)));
+                    // dispatch group (one flag bit each, most frequent first in the kernel) and the shape's index inside it
+                    uint32_t grp = 0, sub = 0;
+                    switch (d.shape) {
+                        case S4x4: grp = REC_G4x4; break;
+                        case S8x4: grp = REC_GA32; sub = 0; break;
+                        case S4x8: grp = REC_GA32; sub = 1; break;
+                        case S8x8: grp = REC_GS1; sub = 0; break;
+                        case S16x4: grp = REC_GS1; sub = 1; break;
+                        case S4x16: grp = REC_GS1; sub = 2; break;
+                        case S32x4: grp = REC_GS1; sub = 3; break;
+                        case S4x32: grp = REC_GS1; sub = 4; break;
+                        case S64x64: grp = REC_G64; break;
+                        default: sub = (uint32_t)d.shape - S32x32; break;     // the eight other sizeId-2 shapes
+                    }
+                    if (sub > 7) return cudaErrorInvalidValue;
+                    lanes[hf].push_back(make_uint2((uint32_t)cx | ((uint32_t)cy << 8) | ((uint32_t)mode << 16) | ((uint32_t)part << 24) | (in_range ? REC_INRANGE : 0u) |
+                                                   (in_range && part == 0 ? REC_WRITER : 0u) | grp,
+                                                   coff | (slot << 17) | (sub << 29)));
                 }
                 work[hf].push_back((uint32_t)t | ((uint32_t)w << 8));
                 wcost[hf].push_back(c);
