@@ -73,6 +73,7 @@ constexpr int MAT_BYTES = M0T_OFF + 16 * M0_STRIDE;   // 11200
 // 16 + 16 matrices of a warp 20 banks apart = 8 distinct 4-bank groups used by 4 matrices each = the minimum of 4 wavefronts.
 static_assert(M2_STRIDE % 16 == 0 && M1_STRIDE % 16 == 0 && M0_STRIDE % 16 == 0 && M2T_OFF % 16 == 0 && M1_OFF % 16 == 0 &&
               M1T_OFF % 16 == 0 && M0_OFF % 16 == 0 && M0T_OFF % 16 == 0, "LDS.128 alignment");
+static_assert(M2T_OFF == M2_OFF + 6 * M2_STRIDE && M1T_OFF == M1_OFF + 8 * M1_STRIDE && M0T_OFF == M0_OFF + 16 * M0_STRIDE, "transposed copies follow the plain matrices");
 static_assert((M2_STRIDE / 4) % 32 == 4 && (M1_STRIDE / 4) % 32 == 4 && (M0_STRIDE / 4) % 8 == 4, "bank phases");
 
 constexpr int SM_RED = 0;                                      // first: the TMA box lands here (128-byte aligned)
@@ -159,6 +160,7 @@ struct Ctx {
     uint32_t a_red;           // this thread's column of the [RED_WORDS][NT] scratch (shared-memory address)
     const uint8_t* s_mat;
     int ctuX, tileY;          // frame position of the tile origin
+    bool topEdge, leftEdge;   // the tile touches the frame's first row / first column (uniform over the CTA)
 };
 
 __device__ __forceinline__ int ilog2c(int v) { return v == 1 ? 0 : v == 2 ? 1 : v == 4 ? 2 : v == 8 ? 3 : v == 16 ? 4 : 5; }
@@ -328,15 +330,17 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
     constexpr int UH = W / R, UV = H / R;
 
     // ---- A.1 complete boundaries: pointer + stride into the reference tile (intra.cl:96-107, 232-243)
-    const int absX = c.ctuX + cuX, absY = c.tileY + cuY;
-    uint32_t T, L;      // shared-memory byte addresses of the boundaries' first samples
-    int stT, stL;       // byte stride between samples: 2, or 0 for a replicated sample
-    if (absY > 0) { T = c.a_refT + 2 * ((cuY >> 2) * RT_STRIDE + 8 + cuX); stT = 2; }          // row Y-1 = slot cuY/4
-    else if (absX == 0) { T = c.a_dc; stT = 0; }
-    else { T = c.a_refT + 2 * (RT_ROW0 * RT_STRIDE + 8 + cuX - 1); stT = 0; }                   // F[0][X-1] replicated
-    if (absX > 0) { L = c.a_refL + 2 * ((cuX >> 2) * RL_STRIDE + 8 + cuY); stL = 2; }          // column X-1 = slot cuX/4
-    else if (absY == 0) { L = c.a_dc; stL = 0; }
-    else { L = c.a_refL + 2 * (RL_COL0 * RL_STRIDE + 8 + cuY - 1); stL = 0; }                   // F[Y-1][0] replicated
+    // Inside the frame: row Y-1 is row slot cuY/4, column X-1 is column slot cuX/4.  On the frame's first row / column the
+    // boundary is one replicated sample -- F[0][X-1] resp. F[Y-1][0], or the mid-grey cell in the frame's corner -- read with
+    // stride 0; whether the tile touches those edges at all is uniform over the CTA, so everywhere else the test is one
+    // uniform branch.
+    uint32_t T = c.a_refT + 2 * ((cuY >> 2) * RT_STRIDE + 8 + cuX), L = c.a_refL + 2 * ((cuX >> 2) * RL_STRIDE + 8 + cuY);
+    int stT = 2, stL = 2;      // byte stride between samples: 2, or 0 for a replicated sample
+    if (c.topEdge || c.leftEdge) {
+        const bool atTop = c.topEdge && cuY == 0, atLeft = c.leftEdge && cuX == 0;
+        if (atTop) { T = atLeft ? c.a_dc : c.a_refT + 2 * (RT_ROW0 * RT_STRIDE + 8 + cuX - 1); stT = 0; }
+        if (atLeft) { L = atTop ? c.a_dc : c.a_refL + 2 * (RL_COL0 * RL_STRIDE + 8 + cuY - 1); stL = 0; }
+    }
 
     // ---- A.2 reduced boundaries (intra.cl:127-141, 260-279)
     constexpr int DT = W / B, DL = H / B;
@@ -360,8 +364,6 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
         for (int i = 0; i < B; ++i) { bd[i] = tr ? redL[i] : redT[i]; bd[B + i] = tr ? redT[i] : redL[i]; }
     }
     // ---- A.3 input vector, packed s16x2 for IDP.2A (intra.cl:434-452)
-    const bool tr = mode >= M;
-    const int mat = tr ? mode - M : mode;
     const int first = bd[0];
     // ((32 + sum) >> 6) + first == (32 + 64 * first + sum) >> 6   (intra.cl:454, 481).  For sizeId 1 and 2 everything is
     // carried 4x (inputs and start value): (4 * acc) >> 8 == acc >> 6, and a shift by 8 is a byte selection, so one PRMT
@@ -372,16 +374,19 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
     int ipk[B];
     {
         int in[2 * B];
-        in[0] = (SID == 2) ? 0 : ((c.maxv + 1) >> 1) - first;
+        const int fs = first << SC;
+        in[0] = (SID == 2) ? 0 : (((c.maxv + 1) >> 1) << SC) - fs;
 #pragma unroll
-        for (int i = 1; i < 2 * B; ++i) in[i] = bd[i] - first;
+        for (int i = 1; i < 2 * B; ++i) in[i] = (bd[i] << SC) - fs;        // one shift-and-add each
 #pragma unroll
-        for (int k = 0; k < B; ++k) ipk[k] = ((in[2 * k] << SC) & 0xffff) | (in[2 * k + 1] << (16 + SC));
+        for (int k = 0; k < B; ++k) ipk[k] = __byte_perm(in[2 * k], in[2 * k + 1], 0x5410);   // the low halves of two inputs
     }
+    // the transposed copies of a size's matrices follow the plain ones at the same pitch (static_assert below), and a
+    // transposed mode is M + the matrix number: both kinds sit at offset + mode * pitch
 
     if constexpr (SID == 0) {
         // 4x4: the reduced prediction is the prediction (intra.cl:726-727, 934-935)
-        const uint8_t* mb = c.s_mat + (tr ? M0T_OFF : M0_OFF) + mat * M0_STRIDE;   // row = output position, also for transposed modes
+        const uint8_t* mb = c.s_mat + M0_OFF + mode * M0_STRIDE;   // row = output position, also for transposed modes
         int p[16];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -407,7 +412,7 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
         return;
     } else {
         // ---- A.3 matrix-vector product -> private scratch column, two samples per word
-        const uint8_t* mb = c.s_mat + (SID == 2 ? (tr ? M2T_OFF : M2_OFF) + mat * M2_STRIDE : (tr ? M1T_OFF : M1_OFF) + mat * M1_STRIDE);
+        const uint8_t* mb = c.s_mat + (SID == 2 ? M2_OFF + mode * M2_STRIDE : M1_OFF + mode * M1_STRIDE);
         const char* mp = reinterpret_cast<const char*>(mb);     // matrix rows a*R + b (8 taps each), two per 16-byte load
         uint32_t wp = c.a_red;                                  // words of this lane's scratch column, RED_WB bytes apart
 #pragma unroll 1
@@ -746,6 +751,8 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     c.s_mat = s_mat;
     c.ctuX = ctuX;
     c.tileY = tileY;
+    c.topEdge = tileY == 0;
+    c.leftEdge = ctuX == 0;
 
     // Warp tasks are drawn from a shared-memory counter, one ahead: the record of the next task (one coalesced 8-byte load
     // from a table built once on the host -- the same 870 KB for every CTU, so it lives in L2) is requested before the
@@ -756,17 +763,20 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     // Lane 0 draws.  ptxas wraps an atomic on a warp-uniform address into a vote / popc / shuffle aggregation (17
     // instructions); adding bits of a loaded record that are always 0 -- which the compiler cannot know -- makes the address
     // formally per-lane and leaves a single predicated ATOMS.ADD.
-    const uint2 lr0 = __ldg(&g_lane[half][min(wbeg, MAX_WORK - 1)][lane]);
+    const uint2 lr0 = __ldg(&g_lane[half][min(wbeg, MAX_WORK - 2)][lane]);
     uint32_t a_next, a_dec;
     asm volatile("mov.u32 %0, %1;" : "=r"(a_next) : "r"(smem_u32(s_next) + ((lr0.x >> 5) & 4u)));
     asm volatile("mov.u32 %0, %1;" : "=r"(a_dec) : "r"(smem_u32(s_dec) - 4u * (uint32_t)ordBeg));
+    // the lane's record of the chunk's first task; past the chunk's end a draw reads the half's last row, which is the end mark
+    const char* lane_rec;      // a row of 32 records = 256 bytes; (opaque: the compiler would keep the sum's two terms apart and add them per task)
+    asm volatile("mov.u64 %0, %1;" : "=l"(lane_rec) : "l"(reinterpret_cast<const char*>(&g_lane[half][0][lane]) + (size_t)wbeg * 256));
+    const int end_row = MAX_WORK - 1 - wbeg;
     auto draw = [&]() -> uint2 {
-        int wi;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\tmov.s32 %0, 0;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
+        int wi;     // only lane 0's value is used
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
                      : "=r"(wi) : "r"(lane), "r"(a_next) : "memory");
         wi = __shfl_sync(0xffffffffu, wi, 0);
-        if (wi >= wcnt) return make_uint2(0xffffffffu, 0u);
-        return __ldg(&g_lane[half][wbeg + wi][lane]);
+        return __ldg(reinterpret_cast<const uint2*>(lane_rec + (ptrdiff_t)(wi < wcnt ? wi : end_row) * 256));
     };
     uint2 lr = draw();
     while (lr.x != 0xffffffffu) {
@@ -776,15 +786,51 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const uint32_t x = lr.x;
         const int cuX = x & 0xff, cuY = __byte_perm(x, 0, 0x4441), mode = __byte_perm(x, 0, 0x4442);
         const bool inRange = (x & REC_INRANGE) != 0;
+        const bool writer = (x & REC_WRITER) != 0;
         const uint32_t coff = lr.y & 0x1ffffu;
-        const int slot = (int)((lr.y >> 17) & 0xfffu);
         const uint32_t sub = lr.y >> 29;
         int sad = 0, satd = 0;
         bool active;
-        if ((int)x < 0) active = do_task<0, 4, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd);
-        else if (x & REC_GA32) {
+        // Decision = argmin over the CU's modes, lowest mode wins ties: min of (cost << 6 | mode), cost < 2^24, taken in
+        // registers (REDUX.MIN) and kept per CU in the CTA's shared-memory table.  How the lanes of a task map to CUs
+        // depends on the number of modes, so each dispatch group ends with its own form; lanes that do not vote
+        // (outside the frame, past the type's end) enter as 0xffffffff, the table's initial value.
+        auto dec_key = [&](bool votes) -> uint32_t { return votes ? (((uint32_t)min(2 * sad, satd) << 6) | (uint32_t)mode) : 0xffffffffu; };
+        auto dec_addr = [&]() -> uint32_t { return a_dec + 4u * ((lr.y >> 17) & 0xfffu); };
+        auto decide32 = [&]() {      // 32 modes: the warp is one CU (no lane past the type's end), its slot has a single writer
+            if constexpr (OUT & OUT_DEC) {
+                const uint32_t best = __reduce_min_sync(0xffffffffu, dec_key(active));
+                if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(dec_addr()), "r"(best) : "memory");
+            }
+        };
+        auto decide16 = [&]() {      // 16 modes: each half warp is one CU (or lies past the type's end as a whole)
+            if constexpr (OUT & OUT_DEC) {
+                const uint32_t key = dec_key(writer && active);
+                const bool hi = (lane & 16) != 0;
+                const uint32_t b0 = __reduce_min_sync(0xffffffffu, hi ? 0xffffffffu : key);
+                const uint32_t b1 = __reduce_min_sync(0xffffffffu, hi ? key : 0xffffffffu);
+                if (writer && (lane & 15) == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(dec_addr()), "r"(hi ? b1 : b0) : "memory");
+            }
+        };
+        auto decide12 = [&]() {      // 12 modes: a task spans 3-4 CUs and a CU two tasks -- MATCH.ANY finds the lanes of a CU, one of them does an atomicMin
+            if constexpr (OUT & OUT_DEC) {
+                const bool vote = writer && active;
+                const uint32_t key = dec_key(vote);
+                const int slot = (int)((lr.y >> 17) & 0xfffu);
+                const unsigned grp = __match_any_sync(0xffffffffu, vote ? slot : -1 - lane);
+                if (vote) {
+                    const uint32_t best = __reduce_min_sync(grp, key);
+                    if (lane == __ffs(grp) - 1) asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(dec_addr()), "r"(best) : "memory");
+                }
+            }
+        };
+        if ((int)x < 0) {
+            active = do_task<0, 4, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd);
+            decide32();
+        } else if (x & REC_GA32) {
             if (sub == 0) active = do_task<1, 8, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd);
             else active = do_task<1, 4, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd);
+            decide16();
         } else if (x & REC_GS1) {
             switch (sub) {
                 case 0:  active = do_task<1, 8, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
@@ -793,9 +839,10 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 case 3:  active = do_task<1, 32, 4>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
                 default: active = do_task<1, 4, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
             }
-        } else if (x & REC_G64) active = do_task<2, 64, 64, 4>(c, cuX, cuY, mode, (x >> 24) & 3, inRange, rowsValid, W, sad, satd);
-        else {
-            switch (sub) {
+            decide16();
+        } else {
+            if (x & REC_G64) active = do_task<2, 64, 64, 4>(c, cuX, cuY, mode, (x >> 24) & 3, inRange, rowsValid, W, sad, satd);
+            else switch (sub) {
                 case 0:  active = do_task<2, 32, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
                 case 1:  active = do_task<2, 32, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
                 case 2:  active = do_task<2, 16, 32>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
@@ -805,8 +852,8 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 case 6:  active = do_task<2, 16, 8>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
                 default: active = do_task<2, 8, 16>(c, cuX, cuY, mode, 0, inRange, rowsValid, W, sad, satd); break;
             }
+            decide12();
         }
-        const bool writer = (x & REC_WRITER) != 0;
         if (writer) {
             const uint32_t o = ctuBase + coff;
             const int cost = min(2 * sad, satd);            // intra.cl:1166
@@ -828,30 +875,6 @@ mip_cost_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 }
             }
             if constexpr (OUT & OUT_SADSATD) { g_sad[o] = active ? sad : -1; g_satd[o] = active ? satd : -1; }   // both or neither (launch_costs)
-        }
-        if constexpr (OUT & OUT_DEC) {
-            // decision = argmin over the CU's modes, lowest mode wins ties: min of (cost << 6 | mode), cost < 2^24.
-            // The lanes of one CU are first reduced in registers (MATCH.ANY + REDUX.MIN), then one lane per CU does the
-            // shared-memory atomicMin: 3-4 distinct addresses per warp instead of 32 lanes serialising on them.
-            const bool vote = writer && active;
-            const uint32_t key = ((uint32_t)min(2 * sad, satd) << 6) | (uint32_t)mode;
-            if (x >= REC_GS1) {
-                // 16 or 32 modes (any of the three upper group flags): a CU is exactly one half or one whole warp task (in
-                // range, active and voting as a whole), so its group is known without MATCH and its slot has a single
-                // writer: a plain store
-                const int modes = (int)x < 0 ? 32 : 16;
-                const unsigned grp = modes == 32 ? 0xffffffffu : ((lane & 16) ? 0xffff0000u : 0x0000ffffu);
-                if (vote) {
-                    const uint32_t best = __reduce_min_sync(grp, key);
-                    if ((lane & (modes - 1)) == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_dec + 4u * (uint32_t)slot), "r"(best) : "memory");
-                }
-            } else {
-                const unsigned grp = __match_any_sync(0xffffffffu, vote ? slot : -1 - lane);
-                if (vote) {
-                    const uint32_t best = __reduce_min_sync(grp, key);
-                    if (lane == __ffs(grp) - 1) asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a_dec + 4u * (uint32_t)slot), "r"(best) : "memory");
-                }
-            }
         }
         lr = lr_next;
     }
@@ -1068,7 +1091,8 @@ cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
                         case S64x64: grp = REC_G64; break;
                         default: sub = (uint32_t)d.shape - S32x32; break;     // the eight other sizeId-2 shapes
                     }
-                    if (sub > 7) return cudaErrorInvalidValue;
+                    // the kernel's decision code relies on: 32 modes = one CU per task, 16 modes = one CU per half task
+                    if (sub > 7 || s.modes != (grp == REC_G4x4 ? 32 : (grp & (REC_GA32 | REC_GS1)) ? 16 : 12) || (grp == REC_G4x4 && !in_range)) return cudaErrorInvalidValue;
                     lanes[hf].push_back(make_uint2((uint32_t)cx | ((uint32_t)cy << 8) | ((uint32_t)mode << 16) | ((uint32_t)part << 24) | (in_range ? REC_INRANGE : 0u) |
                                                    (in_range && part == 0 ? REC_WRITER : 0u) | grp,
                                                    coff | (slot << 17) | (sub << 29)));
@@ -1090,7 +1114,7 @@ cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
     for (int sp = 0; sp < 2; ++sp)
         for (int hf = 0; hf < 2; ++hf) {
             const int chunks = chunks_of[sp];
-            if ((int)work[hf].size() > MAX_WORK) return cudaErrorInvalidValue;
+            if ((int)work[hf].size() > MAX_WORK - 2) return cudaErrorInvalidValue;   // the last row is the end mark
             double total = 0;
             for (double c : wcost[hf]) total += c;
             begin[sp][hf][0] = 0;
@@ -1107,8 +1131,11 @@ cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
         }
     if (mip_compact_type_offset(MIP_NUM_TYPES) != MIP_COMPACT_BYTES_PER_CTU) return cudaErrorInvalidValue;
     if ((err = cudaMemcpyToSymbol(c_types, types, sizeof(types))) != cudaSuccess) return err;
-    for (int hf = 0; hf < 2; ++hf)
+    const std::vector<uint2> end_mark(32, make_uint2(0xffffffffu, 0u));
+    for (int hf = 0; hf < 2; ++hf) {
         if ((err = cudaMemcpyToSymbol(g_lane, lanes[hf].data(), lanes[hf].size() * sizeof(uint2), (size_t)hf * MAX_WORK * 32 * sizeof(uint2))) != cudaSuccess) return err;
+        if ((err = cudaMemcpyToSymbol(g_lane, end_mark.data(), 32 * sizeof(uint2), ((size_t)hf * MAX_WORK + MAX_WORK - 1) * 32 * sizeof(uint2))) != cudaSuccess) return err;
+    }
     if ((err = cudaMemcpyToSymbol(c_chunk_begin, begin, sizeof(begin))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_chunks, chunks_of, sizeof(chunks_of))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_chunk_ord, chunk_ord, sizeof(chunk_ord))) != cudaSuccess) return err;
