@@ -415,7 +415,9 @@ __device__ __forceinline__ void run_task(const Ctx& c, int cuX, int cuY, int mod
         const uint8_t* mb = c.s_mat + (SID == 2 ? M2_OFF + mode * M2_STRIDE : M1_OFF + mode * M1_STRIDE);
         const char* mp = reinterpret_cast<const char*>(mb);     // matrix rows a*R + b (8 taps each), two per 16-byte load
         uint32_t wp = c.a_red;                                  // words of this lane's scratch column, RED_WB bytes apart
-#pragma unroll 1
+        // rolled, because the kernel lives on the instruction caches' good will; two rows per trip for the 4x4 reduced
+        // prediction, whose row is only two stores long (measured: 1 % of the frame; unrolling further, or the block loops, costs more than it saves)
+#pragma unroll (R == 4 ? 2 : 1)
         for (int a = 0; a < R; ++a) {
 #pragma unroll
             for (int b = 0; b < R; b += 2) {
