@@ -431,7 +431,26 @@ def main():
     e2e_cmp_s = wl.host_path(mipb200.EMIT_COSTS_COMPACT | mipb200.EMIT_DECISIONS, False, e2e_steps)
     pool_np = wl.pool_np
     wl.free()
-    dev_ms, e2e_ms, e2e_dec_ms, kernel_ms, e2e_cmp_ms = max_over_ranks([dev_ms, e2e_s * 1e3, e2e_dec_s * 1e3, kernel_ms, e2e_cmp_s * 1e3])
+
+    # what the box's host link gives a plain read-back of the same bytes (one frame's table + decisions, device -> page-locked
+    # host memory, back to back on one stream, all ranks at once): the ceiling of `e2e_costs` on THIS box, whatever the kernel
+    d2h_frame_bytes = 4 * GEOM[(W, H)]["n_ctus"] * COSTS_PER_CTU + 5 * GEOM[(W, H)]["n_ctus"] * CUS_PER_CTU
+    link_src = torch.empty(d2h_frame_bytes, dtype=torch.uint8, device="cuda")
+    link_dst = [torch.empty(d2h_frame_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    link_n = 24
+    for i in range(4):
+        link_dst[i & 1].copy_(link_src, non_blocking=True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(link_n):
+        link_dst[i & 1].copy_(link_src, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    link_ms = ev0.elapsed_time(ev1)
+    del link_src, link_dst
+    dev_ms, e2e_ms, e2e_dec_ms, kernel_ms, e2e_cmp_ms, link_ms = max_over_ranks([dev_ms, e2e_s * 1e3, e2e_dec_s * 1e3, kernel_ms, e2e_cmp_s * 1e3, link_ms])
+    link_fps = link_n * world / (link_ms * 1e-3)
     value = B * args.steps * world / (dev_ms * 1e-3)
     e2e_fps = B * e2e_steps * world / (e2e_ms * 1e-3)
     e2e_dec_fps = B * e2e_steps * world / (e2e_dec_ms * 1e-3)
@@ -468,7 +487,9 @@ def main():
         frame_bytes = 2 * W * H
         d2h_frame = 4 * g["n_ctus"] * COSTS_PER_CTU + 5 * g["n_ctus"] * CUS_PER_CTU
         e2e_costs = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * d2h_frame,
-                     "result": "decisions + the full int32 cost table (the reference's minSadHad readback, 52.8 MB per frame)"}
+                     "result": "decisions + the full int32 cost table (the reference's minSadHad readback, 52.8 MB per frame)",
+                     "d2h_link": {"what": "plain cudaMemcpyAsync of one frame's results (device -> page-locked host), back to back, measured in this run on this box: the ceiling of this number",
+                                  "gbs_per_gpu": d2h_frame_bytes * link_n / (link_ms * 1e-3) / 1e9, "ceiling": link_fps, "unit": "frames/s", "frac": e2e_fps / link_fps}}
         line = {
             "metric": "1080p frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",

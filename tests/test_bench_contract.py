@@ -51,4 +51,6 @@ def test_gpu_arm_json_line():
     assert 0.3 < rf["lone_frame"]["frac"] <= rf["frac"] * 1.02 and rf["traffic"] > rf["hbm"]["algorithmic_bytes_per_launch"]
     assert line["shard_check"]["status"] == "ok" and len(line["sizes"]) == 2 and all(s["value"] > 50 for s in line["sizes"])
     assert line["e2e_like_for_like"]["value"] == line["e2e_costs"]["value"] > 300
+    link = line["e2e_costs"]["d2h_link"]          # the box's read-back ceiling, measured in the same run
+    assert link["gbs_per_gpu"] > 10 and 0.5 < link["frac"] <= 1.02 and abs(link["frac"] - line["e2e_costs"]["value"] / link["ceiling"]) < 1e-9
     assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"} and "workload" in line["config"]
