@@ -39,6 +39,7 @@
 #include "mip_filters.h"
 #include "mip_matrices.h"
 #include "mip_tables.h"
+#include "mip_work_list.h"
 
 namespace mipb200 {
 
@@ -55,7 +56,6 @@ constexpr int OS = 132;                 // s_orig row stride in int32 words (128
 // column -1, columns 3,7,..,127, frame column 0), the columns stored transposed so that a left boundary is contiguous.
 constexpr int RT_STRIDE = 136, RT_SLOTS = 18, RT_ROW0 = 17;   // row slot: [x + 8], x = -8..127
 constexpr int RL_STRIDE = 72, RL_SLOTS = 34, RL_COL0 = 33;    // column slot: [y + 8], y = -8..63
-constexpr int TILE_ROWS = 64;            // a CTA works on the top or bottom half of a CTU
 constexpr int RED_WORDS = 32;           // packed reduced-prediction words per thread (64 samples)
 
 // Every matrix is kept twice: as is, and with its rows permuted by the transposition p = y*r + x -> x*r + y, so that
@@ -94,8 +94,6 @@ constexpr int STG_BYTES = STG_W * STG_H * 2;                   // 19872
 static_assert(STG_BYTES <= SM_RED_BYTES, "staging tile must fit into the scratch it overlays");
 static_assert(SM_RED % 128 == 0, "TMA destination must be 128-byte aligned");
 
-constexpr int MAX_CHUNKS = 64;
-constexpr int MAX_WORK = 1700;          // warp tasks per CTU half
 
 struct DevType {               // what device code needs to know about a CU type; everything positional is in g_lane
     uint8_t w, h, modes, shape;
@@ -111,39 +109,13 @@ __constant__ DevType c_types[MIP_NUM_TYPES];
 __constant__ int c_chunks[2];
 __constant__ int c_chunk_begin[2][2][MAX_CHUNKS + 1];
 // fused decisions: a chunk never splits the modes of a CU, so the CTA owns the argmin of its CUs
-constexpr int DEC_MAX = 2048;                  // CUs per chunk the shared-memory argmin table can hold
 __constant__ uint16_t c_chunk_ord[2][2][MAX_CHUNKS + 1];   // first CU ordinal of each chunk (per split and half)
-__constant__ uint16_t c_ord2cu[2][2700];       // CU ordinal inside a half -> CU index inside the CTU (0..5379)
+__constant__ uint16_t c_ord2cu[2][MAX_ORD];       // CU ordinal inside a half -> CU index inside the CTU (0..5379)
 __device__ uint2 g_lane[2][MAX_WORK][32];      // per (half, warp task, lane): what the lane does, see the task loop of mip_cost_kernel
-// Lane record: .x = cuX (byte 0; bit 7 is never set) | cuY (byte 1) | mode (byte 2) | strip group << 24 | flags, .y = cost index
-// in the CTU | decision slot << 17 | index of the shape inside its dispatch group << 29.  0xffffffff in .x = no more work.
-// Fields sit on byte boundaries (one PRMT each), flags are tested in place, and the CU shape is a prefix code -- one flag
-// bit per group, the most frequent group first -- instead of a number to be looked up in a 17-way switch.
-constexpr uint32_t REC_INRANGE = 1u << 26;     // the lane holds a real (CU, mode)
-constexpr uint32_t REC_WRITER = 1u << 27;      // ... and is the one that writes its cost (strip group 0)
-constexpr uint32_t REC_G64 = 1u << 28;         // 64x64 (12 modes, four lanes per (CU, mode))
-constexpr uint32_t REC_GS1 = 1u << 29;         // 8x8, 16x4, 4x16, 32x4, 4x32 (16 modes)
-constexpr uint32_t REC_GA32 = 1u << 30;        // 8x4, 4x8 (16 modes)
-constexpr uint32_t REC_G4x4 = 1u << 31;        // 4x4 (32 modes)
+// (lane-record layout, the REC_* flags and the CU shapes: mip_work_list.h)
 __device__ uint8_t g_mat[MAT_BYTES];           // (coef - 32) as signed bytes, padded layout above
 
 static int g_chunks[2] = {0, 0};
-
-// the 17 distinct CU shapes
-enum Shape {
-    S64x64, S32x32, S32x16, S16x32, S32x8, S8x32, S16x16, S16x8, S8x16,  // sizeId 2
-    S32x4, S4x32, S16x4, S4x16, S8x8, S8x4, S4x8,                        // sizeId 1
-    S4x4,                                                                // sizeId 0
-    NUM_SHAPES
-};
-
-static int shape_of(int w, int h) {
-    static const int tab[NUM_SHAPES][2] = {{64, 64}, {32, 32}, {32, 16}, {16, 32}, {32, 8}, {8, 32}, {16, 16}, {16, 8}, {8, 16},
-                                           {32, 4},  {4, 32},  {16, 4},  {4, 16},  {8, 8},  {8, 4},  {4, 8},   {4, 4}};
-    for (int i = 0; i < NUM_SHAPES; ++i)
-        if (tab[i][0] == w && tab[i][1] == h) return i;
-    return -1;
-}
 
 // ------------------------------------------------------------------------------------------
 // Device helpers
@@ -1028,120 +1000,35 @@ static const void* cost_kernel_variant(int v) {
 }
 
 cudaError_t kernels_init(const int* nchunks, const double* const* weights) {
-    // cum[sp][k] = share of a half's cost that lies before chunk k of split sp (equal shares unless weights are given)
-    double cum[2][MAX_CHUNKS + 1];
-    int chunks_of[2];
-    for (int sp = 0; sp < 2; ++sp) {
-        const int chunks = chunks_of[sp] = std::min(std::max(nchunks[sp], 1), MAX_CHUNKS);
-        double wsum = 0;
-        for (int k = 0; k < chunks; ++k) wsum += weights[sp] ? weights[sp][k] : 1.0;
-        cum[sp][0] = 0;
-        for (int k = 0; k < chunks; ++k) cum[sp][k + 1] = cum[sp][k] + (weights[sp] ? weights[sp][k] : 1.0) / wsum;
-    }
     cudaError_t err;
-    // CU tables
+    // the work list (mip_work_list.h: lane records, CU ordinals, the two chunk splits) and the CU type table
+    static WorkList wl;
+    if (!build_work_list(wl) || !split_work_list(wl, nchunks, weights)) return cudaErrorInvalidValue;
     DevType types[MIP_NUM_TYPES];
     memset(types, 0, sizeof(types));
-    std::vector<uint32_t> work[2];
-    std::vector<uint2> lanes[2];          // 32 lane records per warp task
-    std::vector<double> wcost[2];
-    std::vector<char> cut_ok[2];          // may a chunk boundary follow this warp task? (no CU's modes may be split)
-    std::vector<int> ord_after[2];        // CU ordinal reached after this warp task (valid where cut_ok)
-    static uint16_t ord2cu[2][2700];
-    int ord_total[2] = {0, 0};
     for (int t = 0; t < MIP_NUM_TYPES; ++t) {
         const mip_cu_type_t& s = MIP_TYPES[t];
         DevType& d = types[t];
         d.w = s.w; d.h = s.h; d.modes = s.modes;
-        d.shape = (uint8_t)shape_of(s.w, s.h);
+        d.shape = wl.shape[t];
         d.cost_off = s.cost_off; d.cu_off = s.cu_off;
-        d.parts_log2 = (s.w == 64 && s.h == 64) ? 2 : 0;
+        d.parts_log2 = wl.parts_log2[t];
         d.narrow = (uint8_t)mip_compact_narrow(t);
         d.cmp_off = (uint32_t)mip_compact_type_offset(t);
-        // CUs per CTU half: CU order is raster, so each half is one contiguous run; no CU crosses y = 64
-        for (int hf = 0; hf < 2; ++hf) {
-            int first = -1, cnt = 0;
-            for (int cu = 0; cu < s.n; ++cu) {
-                const int y = s.ys[cu / s.cols];
-                if (y / 64 != (y + s.h - 1) / 64) return cudaErrorInvalidValue;
-                if (y / 64 == hf) { if (first < 0) first = cu; else if (cu != first + cnt) return cudaErrorInvalidValue; cnt++; }
-            }
-            const int first_cu = first < 0 ? 0 : first;
-            const double mv = s.size_id == 2 ? 700.0 : (s.size_id == 1 ? 200.0 : 120.0);
-            const double c = (mv + 11.0 * s.w * s.h + 2.0 * (s.w + s.h) + 60.0) / (1 << d.parts_log2) + (d.parts_log2 ? mv : 0.0);
-            const int per_cu = s.modes << d.parts_log2, ntask = cnt * per_cu;
-            const int nw = (ntask + 31) / 32;
-            for (int w = 0; w < nw; ++w) {
-                for (int lane = 0; lane < 32; ++lane) {
-                    const int task = w * 32 + lane, in_range = task < ntask, tcl = in_range ? task : ntask - 1;
-                    const int part = tcl & ((1 << d.parts_log2) - 1), cm = tcl >> d.parts_log2;
-                    const int cu_local = cm / s.modes, mode = cm % s.modes, cu = first_cu + cu_local;
-                    const int cx = s.xs[cu % s.cols], cy = s.ys[cu / s.cols] - hf * TILE_ROWS;
-                    const uint32_t coff = s.cost_off + (uint32_t)cu * s.modes + mode, slot = (uint32_t)(ord_total[hf] + cu_local);
-                    if (cx > 127 || cy < 0 || cy > 63 || mode > 31 || part > 3 || coff >= (1u << 17) || slot >= (1u << 12)) return cudaErrorInvalidValue;
-                    // dispatch group (one flag bit each, most frequent first in the kernel) and the shape's index inside it
-                    uint32_t grp = 0, sub = 0;
-                    switch (d.shape) {
-                        case S4x4: grp = REC_G4x4; break;
-                        case S8x4: grp = REC_GA32; sub = 0; break;
-                        case S4x8: grp = REC_GA32; sub = 1; break;
-                        case S8x8: grp = REC_GS1; sub = 0; break;
-                        case S16x4: grp = REC_GS1; sub = 1; break;
-                        case S4x16: grp = REC_GS1; sub = 2; break;
-                        case S32x4: grp = REC_GS1; sub = 3; break;
-                        case S4x32: grp = REC_GS1; sub = 4; break;
-                        case S64x64: grp = REC_G64; break;
-                        default: sub = (uint32_t)d.shape - S32x32; break;     // the eight other sizeId-2 shapes
-                    }
-                    // the kernel's decision code relies on: 32 modes = one CU per task, 16 modes = one CU per half task
-                    if (sub > 7 || s.modes != (grp == REC_G4x4 ? 32 : (grp & (REC_GA32 | REC_GS1)) ? 16 : 12) || (grp == REC_G4x4 && !in_range)) return cudaErrorInvalidValue;
-                    lanes[hf].push_back(make_uint2((uint32_t)cx | ((uint32_t)cy << 8) | ((uint32_t)mode << 16) | ((uint32_t)part << 24) | (in_range ? REC_INRANGE : 0u) |
-                                                   (in_range && part == 0 ? REC_WRITER : 0u) | grp,
-                                                   coff | (slot << 17) | (sub << 29)));
-                }
-                work[hf].push_back((uint32_t)t | ((uint32_t)w << 8));
-                wcost[hf].push_back(c);
-                const int done = std::min(ntask, 32 * (w + 1));
-                cut_ok[hf].push_back(done % per_cu == 0);
-                ord_after[hf].push_back(ord_total[hf] + done / per_cu);
-            }
-            for (int k = 0; k < cnt; ++k) ord2cu[hf][ord_total[hf] + k] = (uint16_t)(s.cu_off + first_cu + k);
-            ord_total[hf] += cnt;
-            if (ord_total[hf] > 2700) return cudaErrorInvalidValue;
-        }
     }
-    // contiguous, cost-balanced partition of each half's work list into chunks, once per split
-    static int begin[2][2][MAX_CHUNKS + 1];
-    static uint16_t chunk_ord[2][2][MAX_CHUNKS + 1];
-    for (int sp = 0; sp < 2; ++sp)
-        for (int hf = 0; hf < 2; ++hf) {
-            const int chunks = chunks_of[sp];
-            if ((int)work[hf].size() > MAX_WORK - 2) return cudaErrorInvalidValue;   // the last row is the end mark
-            double total = 0;
-            for (double c : wcost[hf]) total += c;
-            begin[sp][hf][0] = 0;
-            double acc = 0;
-            int k = 1;
-            chunk_ord[sp][hf][0] = 0;
-            for (size_t i = 0; i < work[hf].size() && k < chunks; ++i) {
-                acc += wcost[hf][i];
-                if (acc >= total * cum[sp][k] && cut_ok[hf][i]) { chunk_ord[sp][hf][k] = (uint16_t)ord_after[hf][i]; begin[sp][hf][k++] = (int)i + 1; }
-            }
-            while (k <= MAX_CHUNKS) { chunk_ord[sp][hf][k] = (uint16_t)ord_total[hf]; begin[sp][hf][k++] = (int)work[hf].size(); }
-            for (int q = 0; q < chunks; ++q)
-                if (chunk_ord[sp][hf][q + 1] - chunk_ord[sp][hf][q] > DEC_MAX) return cudaErrorInvalidValue;   // use more chunks
-        }
+    static_assert(sizeof(LaneRec) == sizeof(uint2), "a lane record is a uint2 on the device");
     if (mip_compact_type_offset(MIP_NUM_TYPES) != MIP_COMPACT_BYTES_PER_CTU) return cudaErrorInvalidValue;
     if ((err = cudaMemcpyToSymbol(c_types, types, sizeof(types))) != cudaSuccess) return err;
-    const std::vector<uint2> end_mark(32, make_uint2(0xffffffffu, 0u));
+    const std::vector<LaneRec> end_mark(32, LaneRec{0xffffffffu, 0u});
     for (int hf = 0; hf < 2; ++hf) {
-        if ((err = cudaMemcpyToSymbol(g_lane, lanes[hf].data(), lanes[hf].size() * sizeof(uint2), (size_t)hf * MAX_WORK * 32 * sizeof(uint2))) != cudaSuccess) return err;
-        if ((err = cudaMemcpyToSymbol(g_lane, end_mark.data(), 32 * sizeof(uint2), ((size_t)hf * MAX_WORK + MAX_WORK - 1) * 32 * sizeof(uint2))) != cudaSuccess) return err;
+        if ((err = cudaMemcpyToSymbol(g_lane, wl.lanes[hf].data(), wl.lanes[hf].size() * sizeof(LaneRec), (size_t)hf * MAX_WORK * 32 * sizeof(uint2))) != cudaSuccess) return err;
+        if ((err = cudaMemcpyToSymbol(g_lane, end_mark.data(), 32 * sizeof(LaneRec), ((size_t)hf * MAX_WORK + MAX_WORK - 1) * 32 * sizeof(uint2))) != cudaSuccess) return err;
     }
-    if ((err = cudaMemcpyToSymbol(c_chunk_begin, begin, sizeof(begin))) != cudaSuccess) return err;
-    if ((err = cudaMemcpyToSymbol(c_chunks, chunks_of, sizeof(chunks_of))) != cudaSuccess) return err;
-    if ((err = cudaMemcpyToSymbol(c_chunk_ord, chunk_ord, sizeof(chunk_ord))) != cudaSuccess) return err;
-    if ((err = cudaMemcpyToSymbol(c_ord2cu, ord2cu, sizeof(ord2cu))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_chunk_begin, wl.begin, sizeof(wl.begin))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_chunks, wl.chunks, sizeof(wl.chunks))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_chunk_ord, wl.chunk_ord, sizeof(wl.chunk_ord))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_ord2cu, wl.ord2cu, sizeof(wl.ord2cu))) != cudaSuccess) return err;
+    const int* chunks_of = wl.chunks;
     // matrices: (coef - 32) as signed bytes in the padded shared-memory layout
     std::vector<uint8_t> mat(MAT_BYTES, 0);
     auto tpos = [](int p, int r) { return (p % r) * r + p / r; };   // output position of matrix row p in a transposed mode (intra.cl:485-487)
